@@ -1,0 +1,407 @@
+// rt_env.cu — host side of the batched environment: handle, device slab, launches, C ABI.
+// See include/rt_b200.h for the contract of every entry point.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "rt_env_kernels.cuh"
+#include "rt_host.h"
+
+using namespace rt;
+
+struct rt_env {
+  rt_env_cfg cfg;
+  EnvDev dev;
+  int device = 0;
+  int n_sm = 148;
+  void* slab = nullptr;  // one allocation, carved at 256 B granularity
+  size_t slab_bytes = 0;
+  void* buf_ptr[RT_BUF__COUNT] = {};
+  size_t buf_bytes[RT_BUF__COUNT] = {};
+  // host-facing variants: device mirrors + pinned staging of the small per-agent arrays
+  int32_t* d_actions = nullptr;
+  int32_t* d_obs_xy = nullptr;
+  int32_t* d_reward = nullptr;
+  uint8_t* d_done = nullptr;
+  uint8_t* d_mask = nullptr;
+  unsigned char* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  int32_t* d_flag_or = nullptr;
+  int64_t launches = 0;
+  int epb = 64;
+  bool lut_in_smem = true;
+};
+
+namespace {
+
+struct Carver {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    const size_t at = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return at;
+  }
+};
+
+bool is_pinned_or_device(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged ||
+         at.type == cudaMemoryTypeDevice;
+}
+
+__global__ void k_or_flags(const int32_t* __restrict__ flags, int n, int32_t* __restrict__ out) {
+  int v = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v |= flags[i];
+  v = __reduce_or_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0 && v) atomicOr(out, v);
+}
+
+int launch_raster(rt_env* h, float* obs_maps, cudaStream_t st) {
+  const EnvDev& d = h->dev;
+  if ((d.cells & 7) == 0) {
+    const long long n_chunks = (long long)d.E * (d.cells >> 3);
+    const int threads = 256;
+    long long blocks = (n_chunks + threads - 1) / threads;
+    const long long cap_blocks = (long long)h->n_sm * 8 * 4;  // a few waves of 8 resident CTAs / SM
+    if (blocks > cap_blocks) blocks = cap_blocks;
+    if (h->lut_in_smem)
+      k_raster_vec<true><<<(unsigned)blocks, threads, (size_t)(d.cap + 1) * 4, st>>>(d, obs_maps, n_chunks);
+    else
+      k_raster_vec<false><<<(unsigned)blocks, threads, 0, st>>>(d, obs_maps, n_chunks);
+  } else {
+    const long long n = (long long)d.E * d.cells;
+    long long blocks = (n + 255) / 256;
+    if (blocks > (long long)h->n_sm * 32) blocks = (long long)h->n_sm * 32;
+    k_raster_any<<<(unsigned)blocks, 256, 0, st>>>(d, obs_maps, n);
+  }
+  h->launches += 1;
+  RT_CUDA_LAUNCH_CHECK();
+  return RT_OK;
+}
+
+int launch_step(rt_env* h, const int32_t* actions, int32_t* obs_xy, float* obs_maps, int32_t* reward,
+                uint8_t* done, cudaStream_t st) {
+  const EnvDev& d = h->dev;
+  const int epb = h->epb;
+  const unsigned blocks = (unsigned)((d.E + epb - 1) / epb);
+  k_step<<<blocks, epb * d.A, step_smem_bytes(epb, d.A), st>>>(d, actions, obs_xy, reward, done);
+  h->launches += 1;
+  RT_CUDA_LAUNCH_CHECK();
+  if (obs_maps) return launch_raster(h, obs_maps, st);
+  return RT_OK;
+}
+
+int launch_reset(rt_env* h, const uint8_t* mask, int32_t* obs_xy, float* obs_maps, cudaStream_t st) {
+  const EnvDev& d = h->dev;
+  k_reset_state<<<(unsigned)((d.E + 127) / 128), 128, 0, st>>>(d, mask, obs_xy);
+  k_zero_maps<<<(unsigned)d.E, 256, 0, st>>>(d, mask);
+  h->launches += 2;
+  RT_CUDA_LAUNCH_CHECK();
+  if (obs_maps) return launch_raster(h, obs_maps, st);
+  return RT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rt_abi_version(void) { return RT_ABI_VERSION; }
+
+const char* rt_status_string(int status) {
+  switch (status) {
+    case RT_OK: return "ok";
+    case RT_ERR_BAD_ARG: return "bad argument";
+    case RT_ERR_CUDA: return rt_last_cuda_error();
+    case RT_ERR_NOMEM: return "out of memory";
+    case RT_ERR_BAD_ACTION: return "action outside 1..4";
+    case RT_ERR_ASSERT: return "reference assertion";
+    case RT_ERR_KEY: return "key does not exist";
+    default: return "unknown status";
+  }
+}
+
+int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
+  if (!cfg || !out) return RT_ERR_BAD_ARG;
+  *out = nullptr;
+  const long long cap = (long long)cfg->max_steps * cfg->n_agents;
+  if (cfg->n_envs < 1 || cfg->n_agents < 1 || cfg->n_agents > RT_MAX_AGENTS || cfg->grid < 2 ||
+      cfg->grid > 256 || cfg->max_steps < 1 || cap < 2 || cap > 65534 || cfg->poly_min < 0 ||
+      cfg->poly_max < cfg->poly_min || cfg->poly_max > RT_MAX_POLYS || cfg->lognorm_step < 1 ||
+      !(cfg->cell_pitch_cm > 0.0) || !(cfg->min_dist_cm > 0.0) || !(cfg->transmission >= 0.0) ||
+      (cfg->poly_max > 0 && (cfg->rect_min < 1 || cfg->rect_max < cfg->rect_min)))
+    return RT_ERR_BAD_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    rt_note_cuda_error(cudaGetLastError(), "cudaGetDeviceCount");
+    return RT_ERR_CUDA;  // no CPU fallback, by design
+  }
+  rt_env* h = new (std::nothrow) rt_env();
+  if (!h) return RT_ERR_NOMEM;
+  h->cfg = *cfg;
+  RT_CUDA_OR(cudaGetDevice(&h->device), { delete h; });
+  cudaDeviceProp prop;
+  RT_CUDA_OR(cudaGetDeviceProperties(&prop, h->device), { delete h; });
+  h->n_sm = prop.multiProcessorCount;
+
+  const size_t E = (size_t)cfg->n_envs, A = (size_t)cfg->n_agents;
+  const size_t cells = (size_t)cfg->grid * cfg->grid;
+  const size_t sz[RT_BUF__COUNT] = {
+      /*AGENT_XY*/ E * A * 8,   /*PREV_DIST*/ E * A * 4, /*START_XY*/ E * A * 8, /*SRC_XY*/ E * 8,
+      /*SRC_INT*/ E * 8,        /*BKG*/ E * 8,           /*N_POLY*/ E * 4,       /*EDGES*/ E * RT_MAX_EDGES * 16,
+      /*TICK*/ E * 4,           /*EPISODE*/ E * 4,       /*VISIT*/ E * cells * 2, /*INTENSITY*/ E * cells * 4,
+      /*HEAD*/ E * cells * 2,   /*LOG*/ (size_t)cap * E * 8, /*unused*/ 0,       /*WELFORD*/ E * 48,
+      /*WELFORD_N*/ E * 4,      /*EST_MAXMIN*/ E * 16,   /*FLAGS*/ E * 4,        /*LAST_COUNT*/ E * A * 4,
+      /*LAST_LOS*/ E * A,       /*LAST_LAMBDA*/ E * A * 8, /*LAST_EST*/ E * A * 8, /*LAST_Z*/ E * A * 8,
+      /*LAST_VALUE*/ E * A * 8, /*VISIT_LUT*/ ((size_t)cap + 1) * 4};
+  Carver cv;
+  size_t off[RT_BUF__COUNT];
+  for (int i = 0; i < RT_BUF__COUNT; ++i) off[i] = cv.take(sz[i]);
+  const size_t o_act = cv.take(E * A * 4), o_xy = cv.take(E * A * 8), o_rw = cv.take(E * A * 4),
+               o_dn = cv.take(E * A), o_mask = cv.take(E), o_for = cv.take(4);
+  h->slab_bytes = cv.off;
+  if (cudaMalloc(&h->slab, h->slab_bytes) != cudaSuccess) {
+    rt_note_cuda_error(cudaGetLastError(), "cudaMalloc(slab)");
+    delete h;
+    return RT_ERR_NOMEM;
+  }
+  RT_CUDA_OR(cudaMemset(h->slab, 0, h->slab_bytes), { cudaFree(h->slab); delete h; });
+  unsigned char* base = (unsigned char*)h->slab;
+  for (int i = 0; i < RT_BUF__COUNT; ++i) {
+    h->buf_ptr[i] = sz[i] ? base + off[i] : nullptr;
+    h->buf_bytes[i] = sz[i];
+  }
+  h->d_actions = (int32_t*)(base + o_act);
+  h->d_obs_xy = (int32_t*)(base + o_xy);
+  h->d_reward = (int32_t*)(base + o_rw);
+  h->d_done = (uint8_t*)(base + o_dn);
+  h->d_mask = (uint8_t*)(base + o_mask);
+  h->d_flag_or = (int32_t*)(base + o_for);
+
+  // pinned staging: actions | obs_xy | reward | done | mask
+  h->pinned_bytes = E * A * 4 + E * A * 8 + E * A * 4 + E * A + E + 64;
+  RT_CUDA_OR(cudaHostAlloc((void**)&h->pinned, h->pinned_bytes, cudaHostAllocDefault),
+             { cudaFree(h->slab); delete h; });
+
+  EnvDev& d = h->dev;
+  d.E = cfg->n_envs; d.A = cfg->n_agents; d.G = cfg->grid; d.cells = (int)cells;
+  d.T = cfg->max_steps; d.cap = (int)cap;
+  d.gid_base = cfg->env_id_base; d.seed = cfg->seed;
+  d.pitch2 = cfg->cell_pitch_cm * cfg->cell_pitch_cm;
+  d.dmin2 = cfg->min_dist_cm * cfg->min_dist_cm;
+  d.transmission = cfg->transmission;
+  d.src_lo = cfg->src_lo; d.src_span = cfg->src_hi - cfg->src_lo;
+  d.bkg_lo = cfg->bkg_lo; d.bkg_span = cfg->bkg_hi - cfg->bkg_lo;
+  d.poly_min = cfg->poly_min; d.poly_max = cfg->poly_max;
+  d.rect_min = cfg->rect_min; d.rect_max = cfg->rect_max; d.fixed = cfg->fixed_scenario;
+  d.agent_xy = (int32_t*)h->buf_ptr[RT_BUF_AGENT_XY];
+  d.prev_dist = (int32_t*)h->buf_ptr[RT_BUF_PREV_DIST];
+  d.start_xy = (int32_t*)h->buf_ptr[RT_BUF_START_XY];
+  d.src_xy = (int32_t*)h->buf_ptr[RT_BUF_SRC_XY];
+  d.src_int = (double*)h->buf_ptr[RT_BUF_SRC_INT];
+  d.bkg = (double*)h->buf_ptr[RT_BUF_BKG];
+  d.n_poly = (int32_t*)h->buf_ptr[RT_BUF_N_POLY];
+  d.edges = (float*)h->buf_ptr[RT_BUF_EDGES];
+  d.tick = (int32_t*)h->buf_ptr[RT_BUF_TICK];
+  d.episode = (int32_t*)h->buf_ptr[RT_BUF_EPISODE];
+  d.visit = (uint16_t*)h->buf_ptr[RT_BUF_VISIT];
+  d.inten = (float*)h->buf_ptr[RT_BUF_INTENSITY];
+  d.head = (uint16_t*)h->buf_ptr[RT_BUF_HEAD];
+  d.log = (uint2*)h->buf_ptr[RT_BUF_LOG];
+  d.welford = (double*)h->buf_ptr[RT_BUF_WELFORD];
+  d.welford_n = (int32_t*)h->buf_ptr[RT_BUF_WELFORD_N];
+  d.est_mm = (double*)h->buf_ptr[RT_BUF_EST_MAXMIN];
+  d.flags = (int32_t*)h->buf_ptr[RT_BUF_FLAGS];
+  d.last_count = (int32_t*)h->buf_ptr[RT_BUF_LAST_COUNT];
+  d.last_los = (uint8_t*)h->buf_ptr[RT_BUF_LAST_LOS];
+  d.last_lambda = (double*)h->buf_ptr[RT_BUF_LAST_LAMBDA];
+  d.last_est = (double*)h->buf_ptr[RT_BUF_LAST_EST];
+  d.last_z = (double*)h->buf_ptr[RT_BUF_LAST_Z];
+  d.last_value = (double*)h->buf_ptr[RT_BUF_LAST_VALUE];
+  d.lut = (float*)h->buf_ptr[RT_BUF_VISIT_LUT];
+  d.inj = nullptr;
+  d.inj_k = 0;
+
+  // episode counters start at -1 so the first reset opens episode 0; Welford std starts at 1
+  {
+    std::vector<int32_t> ep(E, -1);
+    RT_CUDA_OR(cudaMemcpy(d.episode, ep.data(), E * 4, cudaMemcpyHostToDevice),
+               { rt_env_destroy(h); });
+    std::vector<double> w(E * 6, 0.0);
+    for (size_t i = 0; i < E; ++i) w[i * 6 + 3] = 1.0;
+    RT_CUDA_OR(cudaMemcpy(d.welford, w.data(), E * 48, cudaMemcpyHostToDevice), { rt_env_destroy(h); });
+  }
+  // a8: BensLogNormalizer table over every reachable visit count, max = T*A
+  // (normalize.py:64-65,110).  math.log(x, base) is log(x)/log(base); LUT[0] = 0 keeps
+  // never-visited cells dark.
+  {
+    std::vector<float> lut((size_t)cap + 1, 0.0f);
+    const double mx = (double)cap, st = (double)cfg->lognorm_step, lb = std::log(mx);
+    for (long long v = 1; v <= cap; ++v) {
+      const double num = std::log(st + (double)v) / lb;
+      const double den = std::log(st * mx) / lb;
+      const double r = num * 1.0 / den;
+      lut[(size_t)v] = (r >= 0.0 && r <= 1.0) ? (float)r : 1.0f;
+    }
+    RT_CUDA_OR(cudaMemcpy(d.lut, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice),
+               { rt_env_destroy(h); });
+  }
+  h->lut_in_smem = ((size_t)cap + 1) * 4 <= 32 * 1024;
+  // envs per CTA of k_step: <= 256 threads, and enough CTAs to cover the SMs twice when E allows
+  int epb = 256 / cfg->n_agents;
+  if (epb > 64) epb = 64;
+  while (epb > 8 && (cfg->n_envs + epb - 1) / epb < 2 * h->n_sm) epb >>= 1;
+  if (epb * cfg->n_agents < 32) epb = (32 + cfg->n_agents - 1) / cfg->n_agents;
+  h->epb = epb;
+  *out = h;
+  return RT_OK;
+}
+
+int rt_env_destroy(rt_env* h) {
+  if (!h) return RT_OK;
+  if (h->slab) cudaFree(h->slab);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  delete h;
+  return RT_OK;
+}
+
+int rt_env_set_scenario(rt_env* h, const int32_t* src_xy, const double* src_int, const double* bkg,
+                        const int32_t* start_xy, const int32_t* n_poly, const float* edges) {
+  if (!h) return RT_ERR_BAD_ARG;
+  const size_t E = (size_t)h->dev.E, A = (size_t)h->dev.A;
+  if (src_xy)
+    for (size_t i = 0; i < E * 2; ++i)
+      if (src_xy[i] < 0 || src_xy[i] >= h->dev.G) return RT_ERR_BAD_ARG;
+  if (start_xy)
+    for (size_t i = 0; i < E * A * 2; ++i)
+      if (start_xy[i] < 0 || start_xy[i] >= h->dev.G) return RT_ERR_BAD_ARG;
+  if (n_poly)
+    for (size_t i = 0; i < E; ++i)
+      if (n_poly[i] < 0 || n_poly[i] > RT_MAX_POLYS) return RT_ERR_BAD_ARG;
+  if (src_xy) RT_CUDA(cudaMemcpy(h->dev.src_xy, src_xy, E * 8, cudaMemcpyHostToDevice));
+  if (src_int) RT_CUDA(cudaMemcpy(h->dev.src_int, src_int, E * 8, cudaMemcpyHostToDevice));
+  if (bkg) RT_CUDA(cudaMemcpy(h->dev.bkg, bkg, E * 8, cudaMemcpyHostToDevice));
+  if (start_xy) RT_CUDA(cudaMemcpy(h->dev.start_xy, start_xy, E * A * 8, cudaMemcpyHostToDevice));
+  if (n_poly) RT_CUDA(cudaMemcpy(h->dev.n_poly, n_poly, E * 4, cudaMemcpyHostToDevice));
+  if (edges) RT_CUDA(cudaMemcpy(h->dev.edges, edges, E * RT_MAX_EDGES * 16, cudaMemcpyHostToDevice));
+  return RT_OK;
+}
+
+int rt_env_reset(rt_env* h, const uint8_t* mask_dev, int32_t* obs_xy_dev, float* obs_maps_dev,
+                 void* stream) {
+  if (!h) return RT_ERR_BAD_ARG;
+  return launch_reset(h, mask_dev, obs_xy_dev, obs_maps_dev, (cudaStream_t)stream);
+}
+
+int rt_env_step(rt_env* h, const int32_t* actions_dev, int32_t* obs_xy_dev, float* obs_maps_dev,
+                int32_t* reward_dev, uint8_t* done_dev, void* stream) {
+  if (!h || !actions_dev || !obs_xy_dev || !reward_dev || !done_dev) return RT_ERR_BAD_ARG;
+  return launch_step(h, actions_dev, obs_xy_dev, obs_maps_dev, reward_dev, done_dev,
+                     (cudaStream_t)stream);
+}
+
+int rt_env_reset_host(rt_env* h, const uint8_t* mask_host, int32_t* obs_xy_host, float* obs_maps_dev,
+                      void* stream) {
+  if (!h) return RT_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t E = (size_t)h->dev.E, A = (size_t)h->dev.A;
+  const uint8_t* mask_dev = nullptr;
+  if (mask_host) {
+    unsigned char* pm = h->pinned + E * A * 17;
+    const void* srcp = mask_host;
+    if (!is_pinned_or_device(mask_host)) {
+      std::memcpy(pm, mask_host, E);
+      srcp = pm;
+    }
+    RT_CUDA(cudaMemcpyAsync(h->d_mask, srcp, E, cudaMemcpyHostToDevice, st));
+    mask_dev = h->d_mask;
+  }
+  const int rc = launch_reset(h, mask_dev, h->d_obs_xy, obs_maps_dev, st);
+  if (rc != RT_OK) return rc;
+  if (obs_xy_host) {
+    const bool direct = is_pinned_or_device(obs_xy_host);
+    void* dst = direct ? (void*)obs_xy_host : (void*)(h->pinned + E * A * 4);
+    RT_CUDA(cudaMemcpyAsync(dst, h->d_obs_xy, E * A * 8, cudaMemcpyDeviceToHost, st));
+    RT_CUDA(cudaStreamSynchronize(st));
+    if (!direct) std::memcpy(obs_xy_host, dst, E * A * 8);
+  } else {
+    RT_CUDA(cudaStreamSynchronize(st));
+  }
+  return RT_OK;
+}
+
+int rt_env_step_host(rt_env* h, const int32_t* actions_host, int32_t* obs_xy_host, int32_t* reward_host,
+                     uint8_t* done_host, float* obs_maps_dev, void* stream) {
+  if (!h || !actions_host || !obs_xy_host || !reward_host || !done_host) return RT_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)h->dev.E * h->dev.A;
+  unsigned char* p_act = h->pinned;
+  unsigned char* p_xy = h->pinned + n * 4;
+  unsigned char* p_rw = h->pinned + n * 12;
+  unsigned char* p_dn = h->pinned + n * 16;
+  // invalid actions are also caught on the device, but the reference raises before any
+  // state change (simple_gridworld.py:138), so check on the host first
+  for (size_t i = 0; i < n; ++i)
+    if (actions_host[i] < 1 || actions_host[i] > 4) return RT_ERR_BAD_ACTION;
+  const void* a_src = actions_host;
+  if (!is_pinned_or_device(actions_host)) {
+    std::memcpy(p_act, actions_host, n * 4);
+    a_src = p_act;
+  }
+  RT_CUDA(cudaMemcpyAsync(h->d_actions, a_src, n * 4, cudaMemcpyHostToDevice, st));
+  const int rc = launch_step(h, h->d_actions, h->d_obs_xy, obs_maps_dev, h->d_reward, h->d_done, st);
+  if (rc != RT_OK) return rc;
+  const bool dx = is_pinned_or_device(obs_xy_host), dr = is_pinned_or_device(reward_host),
+             dd = is_pinned_or_device(done_host);
+  RT_CUDA(cudaMemcpyAsync(dx ? (void*)obs_xy_host : (void*)p_xy, h->d_obs_xy, n * 8, cudaMemcpyDeviceToHost, st));
+  RT_CUDA(cudaMemcpyAsync(dr ? (void*)reward_host : (void*)p_rw, h->d_reward, n * 4, cudaMemcpyDeviceToHost, st));
+  RT_CUDA(cudaMemcpyAsync(dd ? (void*)done_host : (void*)p_dn, h->d_done, n, cudaMemcpyDeviceToHost, st));
+  RT_CUDA(cudaStreamSynchronize(st));
+  if (!dx) std::memcpy(obs_xy_host, p_xy, n * 8);
+  if (!dr) std::memcpy(reward_host, p_rw, n * 4);
+  if (!dd) std::memcpy(done_host, p_dn, n);
+  return RT_OK;
+}
+
+int rt_env_rasterize(rt_env* h, float* obs_maps_dev, void* stream) {
+  if (!h || !obs_maps_dev) return RT_ERR_BAD_ARG;
+  return launch_raster(h, obs_maps_dev, (cudaStream_t)stream);
+}
+
+int rt_env_inject_uniforms(rt_env* h, const double* u_dev, int32_t k_per_agent) {
+  if (!h || (u_dev && k_per_agent < 1)) return RT_ERR_BAD_ARG;
+  h->dev.inj = u_dev;
+  h->dev.inj_k = u_dev ? k_per_agent : 0;
+  return RT_OK;
+}
+
+int rt_env_buffer(rt_env* h, int which, void** dev_ptr, size_t* bytes) {
+  if (!h || which < 0 || which >= RT_BUF__COUNT || !h->buf_ptr[which]) return RT_ERR_BAD_ARG;
+  if (dev_ptr) *dev_ptr = h->buf_ptr[which];
+  if (bytes) *bytes = h->buf_bytes[which];
+  return RT_OK;
+}
+
+int rt_env_errors(rt_env* h, int32_t* flags_host, void* stream) {
+  if (!h || !flags_host) return RT_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  RT_CUDA(cudaMemsetAsync(h->d_flag_or, 0, 4, st));
+  int blocks = (h->dev.E + 255) / 256;
+  if (blocks > h->n_sm * 8) blocks = h->n_sm * 8;
+  k_or_flags<<<blocks, 256, 0, st>>>(h->dev.flags, h->dev.E, h->d_flag_or);
+  h->launches += 1;
+  RT_CUDA_LAUNCH_CHECK();
+  RT_CUDA(cudaMemcpyAsync(flags_host, h->d_flag_or, 4, cudaMemcpyDeviceToHost, st));
+  RT_CUDA(cudaStreamSynchronize(st));
+  return RT_OK;
+}
+
+int64_t rt_env_launch_count(const rt_env* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

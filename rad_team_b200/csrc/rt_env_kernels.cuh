@@ -1,0 +1,532 @@
+// rt_env_kernels.cuh — the environment kernels of librt_b200.so (sm_100a).
+//
+//   k_step      K1+K2+K4a  motion / collision / reward (simple_gridworld.py:131-167),
+//               measurement (inverse square, line of sight against obstruction edges
+//               staged in shared memory by bulk async copies, Philox Poisson), then the
+//               per-env observation statistics (estimator.py:31-70 -> standardize.py:46-93
+//               -> normalize.py:25-55) and the map cell updates.
+//   k_raster    K3  location / intensity / visit maps -> caller's [E][3][G][G] tensor.
+//   k_reset_*   K5  masked episode reset + scenario generation.
+//
+// HBM layout is structure-of-arrays over envs so that neighbouring threads touch
+// neighbouring addresses; the reading log is time-major [T*A][E] for the same reason.
+#pragma once
+#include <math_constants.h>
+
+#include "rt_device.cuh"
+
+namespace rt {
+
+struct EnvDev {
+  int E, A, G, cells, T, cap;  // cap = T*A log entries per env
+  long long gid_base;
+  unsigned long long seed;
+  double pitch2, dmin2, transmission, src_lo, src_span, bkg_lo, bkg_span;
+  int poly_min, poly_max, rect_min, rect_max, fixed;
+  int32_t* agent_xy;
+  int32_t* prev_dist;
+  int32_t* start_xy;
+  int32_t* src_xy;
+  double* src_int;
+  double* bkg;
+  int32_t* n_poly;
+  float* edges;  // [E][20][4]
+  int32_t* tick;
+  int32_t* episode;
+  uint16_t* visit;  // [E][cells]
+  float* inten;     // [E][cells]
+  uint16_t* head;   // [E][cells]  smallest log entry of the cell, +1 (0 = empty)
+  uint2* log;       // [cap][E]    {count, next larger entry of the same cell + 1}
+  double* welford;  // [E][6]
+  int32_t* welford_n;
+  double* est_mm;  // [E][2]
+  int32_t* flags;
+  int32_t* last_count;
+  uint8_t* last_los;
+  double* last_lambda;
+  double* last_est;
+  double* last_z;
+  double* last_value;
+  float* lut;  // [cap+1]
+  const double* inj;
+  int inj_k;
+};
+
+// --------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + 1-D bulk async copy (the TMA engine without a tensor map; SASS UBLKCP).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(
+                   smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      "RT_WAIT:\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      " @p bra RT_DONE;\n"
+      " bra RT_WAIT;\n"
+      "RT_DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// --------------------------------------------------------------------------------------------
+// K1 + K2 + K4a.  One thread per (env, agent); an env's agents are neighbouring threads of one
+// CTA.  blockDim.x = envs_per_cta * A.
+constexpr int kEdgeRowF4 = RT_MAX_EDGES + 1;  // 21 float4 = 336 B rows: conflict-free float4 reads
+
+struct StepSmem {  // carved from dynamic shared memory, see step_smem_bytes()
+  float4* edges;   // [epb][kEdgeRowF4]
+  int* n_poly;     // [epb]
+  int* skip;       // [epb]  RT_FLAG_* that void this env's step
+  int* eflags;     // [epb]  flags raised by the agents' samplers
+  int* cell;       // [epb*A]
+  int* count;      // [epb*A]
+  uint64_t* bar;
+};
+__host__ __device__ inline size_t step_smem_bytes(int epb, int A) {
+  return 16 + (size_t)epb * kEdgeRowF4 * 16 + (size_t)epb * 3 * 4 + (size_t)epb * A * 2 * 4;
+}
+
+__global__ void __launch_bounds__(256)
+k_step(const EnvDev d, const int32_t* __restrict__ actions, int32_t* __restrict__ obs_xy,
+       int32_t* __restrict__ reward, uint8_t* __restrict__ done) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int A = d.A;
+  const int epb = blockDim.x / A;
+  StepSmem s;
+  s.bar = reinterpret_cast<uint64_t*>(smem_raw);
+  s.edges = reinterpret_cast<float4*>(smem_raw + 16);
+  s.n_poly = reinterpret_cast<int*>(smem_raw + 16 + (size_t)epb * kEdgeRowF4 * 16);
+  s.skip = s.n_poly + epb;
+  s.eflags = s.skip + epb;
+  s.cell = s.eflags + epb;
+  s.count = s.cell + epb * A;
+
+  const int t = threadIdx.x;
+  const int le = t / A;
+  const int a = t - le * A;
+  const int e0 = blockIdx.x * epb;
+  const int e = e0 + le;
+  const bool valid = e < d.E;
+  const int n_valid = min(epb, d.E - e0);
+
+  if (t == 0) mbar_init(s.bar, (uint32_t)n_valid);
+
+  // Independent global loads first: they overlap the barrier set-up and the geometry copy.
+  int act = 1, tick = 0, np = 0;
+  int2 pos = make_int2(0, 0), src = make_int2(0, 0);
+  int pdist = 0;
+  if (valid) {
+    act = actions[(size_t)e * A + a];
+    tick = d.tick[e];
+    pos = reinterpret_cast<const int2*>(d.agent_xy)[(size_t)e * A + a];
+    pdist = d.prev_dist[(size_t)e * A + a];
+    src = reinterpret_cast<const int2*>(d.src_xy)[e];
+    if (a == 0) {
+      np = d.n_poly[e];
+      s.n_poly[le] = np;
+      s.skip[le] = tick >= d.T ? RT_FLAG_LOG_FULL : 0;
+      s.eflags[le] = 0;
+    }
+  }
+  __syncthreads();  // barrier initialised, per-env slots initialised
+
+  if (valid) {
+    if (a == 0) {
+      if (np > 0) {
+        const uint32_t bytes = (uint32_t)np * RT_EDGES_PER_POLY * 16u;
+        mbar_arrive_expect_tx(s.bar, bytes);
+        bulk_g2s(s.edges + (size_t)le * kEdgeRowF4, d.edges + (size_t)e * RT_MAX_EDGES * 4, bytes, s.bar);
+      } else {
+        mbar_arrive(s.bar);
+      }
+    }
+    if (act < 1 || act > 4) atomicOr(&s.skip[le], RT_FLAG_BAD_ACTION);  // simple_gridworld.py:138
+  }
+
+  // a == 0 threads own the per-env statistics; start their loads now.
+  WelfordState w;
+  double emx = 0.0, emn = 0.0, src_int = 0.0, bkg = 0.0;
+  int episode = 0;
+  if (valid) {
+    src_int = d.src_int[e];
+    bkg = d.bkg[e];
+    episode = d.episode[e];
+    if (a == 0) {
+      const double2* wp = reinterpret_cast<const double2*>(d.welford + (size_t)e * 6);
+      const double2 w0 = wp[0], w1 = wp[1], w2 = wp[2];
+      w.mean = w0.x; w.m2 = w0.y; w.var = w1.x; w.sd = w1.y; w.zmax = w2.x; w.zmin = w2.y;
+      w.count = d.welford_n[e];
+      const double2 mm = reinterpret_cast<const double2*>(d.est_mm)[e];
+      emx = mm.x;
+      emn = mm.y;
+    }
+  }
+
+  mbar_wait(s.bar, 0);  // geometry of every env of this CTA has landed in shared memory
+  __syncthreads();      // skip flags complete
+
+  const int skip = valid ? s.skip[le] : 0;
+  if (valid) {
+    const size_t ia = (size_t)e * A + a;
+    if (skip) {  // reference raises before touching state: report the unchanged position
+      reinterpret_cast<int2*>(obs_xy)[ia] = pos;
+      reward[ia] = 0;
+      done[ia] = 0;
+    } else {
+      const float4* my_edges = s.edges + (size_t)le * kEdgeRowF4;
+      np = s.n_poly[le];
+      // a4: agent = clip(agent + direction, 0, size-1)   (simple_gridworld.py:26-31,141)
+      const int dx = (act == 2) - (act == 3);
+      const int dy = (act == 1) - (act == 4);
+      int nx = min(max(pos.x + dx, 0), d.G - 1);
+      int ny = min(max(pos.y + dy, 0), d.G - 1);
+      // N4: refuse a move whose centre-to-centre path crosses an obstruction edge
+      if ((nx != pos.x || ny != pos.y) && np > 0 &&
+          polys_crossed(my_edges, np, (float)pos.x + 0.5f, (float)pos.y + 0.5f, (float)nx + 0.5f,
+                        (float)ny + 0.5f) > 0) {
+        nx = pos.x;
+        ny = pos.y;
+      }
+      // a4: reward / done on the L1 distance to the source cell (:144-159)
+      const int dist = abs(nx - src.x) + abs(ny - src.y);
+      const bool dn = dist <= 1;
+      const int rw = dn ? 1 : (dist < pdist ? 0 : -1);
+      reinterpret_cast<int2*>(d.agent_xy)[ia] = make_int2(nx, ny);
+      d.prev_dist[ia] = dist;
+      reinterpret_cast<int2*>(obs_xy)[ia] = make_int2(nx, ny);
+      reward[ia] = rw;
+      done[ia] = dn ? 1 : 0;
+
+      // N2 + N1: obstructions on the line of sight, expected count
+      const int nb = np > 0 ? polys_crossed(my_edges, np, (float)nx + 0.5f, (float)ny + 0.5f,
+                                            (float)src.x + 0.5f, (float)src.y + 0.5f)
+                            : 0;
+      const int ddx = nx - src.x, ddy = ny - src.y;
+      double d2 = __dmul_rn((double)(ddx * ddx + ddy * ddy), d.pitch2);
+      if (d2 < d.dmin2) d2 = d.dmin2;
+      double strength = src_int;
+      for (int i = 0; i < nb; ++i) strength = __dmul_rn(strength, d.transmission);
+      const double lam = __dadd_rn(__ddiv_rn(strength, d2), bkg);
+
+      // N3: Poisson count
+      Draws dr;
+      dr.init(d.seed, d.gid_base + e, STREAM_MEASURE, a, tick, episode);
+      if (d.inj != nullptr) {
+        dr.inj = d.inj + ((size_t)e * A + a) * (size_t)d.inj_k;
+        dr.inj_k = d.inj_k;
+      }
+      int fl = 0;
+      const long long cnt = poisson_draw(lam, dr, fl);
+      if (fl) atomicOr(&s.eflags[le], fl);
+
+      s.cell[t] = ny * d.G + nx;
+      s.count[t] = (int)cnt;
+      d.last_count[ia] = (int)cnt;
+      d.last_los[ia] = (uint8_t)nb;
+      d.last_lambda[ia] = lam;
+    }
+  }
+  __syncthreads();  // readings of all agents are in shared memory
+
+  if (!valid || a != 0) return;
+  if (skip) {
+    atomicOr(&d.flags[e], skip);
+    return;
+  }
+  // K4a: the env's agents feed ONE estimator / Welford / normaliser, in agent order.
+  uint16_t* visit = d.visit + (size_t)e * d.cells;
+  uint16_t* head = d.head + (size_t)e * d.cells;
+  float* inten = d.inten + (size_t)e * d.cells;
+  uint2* log = d.log + e;  // entry i at log[i * E]
+  const size_t E = (size_t)d.E;
+  int fl = s.eflags[le];
+  for (int aa = 0; aa < A; ++aa) {
+    const int cell = s.cell[le * A + aa];
+    const int cnt = s.count[le * A + aa];
+    const int idx = tick * A + aa;
+    const int n = (int)visit[cell] + 1;  // readings at this cell including this one
+    visit[cell] = (uint16_t)n;
+
+    // a9: IntensityResamplingEstimator.update + get_estimate (estimator.py:31-48,61-70).
+    // The cell's readings form a linked list sorted by value; insert the new reading and
+    // pick the median (elements (n-1)/2 and n/2 of the new list) in the same walk.
+    const int k1 = (n - 1) >> 1, k2 = n >> 1;
+    int cur = (int)head[cell];  // encoded idx+1, 0 = end
+    int pred = 0;
+    bool inserted = false;
+    int m1 = 0, m2 = 0;
+    uint2 nd = make_uint2(0u, 0u);
+    bool have = false;
+    for (int i = 0; i <= k2 || !inserted; ++i) {
+      if (cur != 0 && !have) {
+        nd = log[(size_t)(cur - 1) * E];
+        have = true;
+      }
+      int elem;
+      if (!inserted && (cur == 0 || (int)nd.x > cnt)) {
+        elem = cnt;
+        inserted = true;
+        log[(size_t)idx * E] = make_uint2((uint32_t)cnt, (uint32_t)cur);
+        if (pred == 0)
+          head[cell] = (uint16_t)(idx + 1);
+        else
+          log[(size_t)(pred - 1) * E].y = (uint32_t)(idx + 1);
+      } else {
+        elem = (int)nd.x;
+        pred = cur;
+        cur = (int)nd.y;
+        have = false;
+      }
+      if (i == k1) m1 = elem;
+      if (i == k2) m2 = elem;
+    }
+    const double est = (n & 1) ? (double)m2 : __ddiv_rn((double)((long long)m1 + (long long)m2), 2.0);
+    est_maxmin(est, emx, emn);
+
+    // a6: Welford update + z-score; a7: min-max against the running z range
+    const double z = welford_update(w, est);
+    double val;
+    if (!normalize_minmax(z, w.zmax, true, w.zmin, val)) {
+      fl |= RT_FLAG_NORMALIZE;
+      val = 0.0;
+    }
+    inten[cell] = (float)val;
+    const size_t ia = (size_t)e * A + aa;
+    d.last_est[ia] = est;
+    d.last_z[ia] = z;
+    d.last_value[ia] = val;
+  }
+  double2* wp = reinterpret_cast<double2*>(d.welford + (size_t)e * 6);
+  wp[0] = make_double2(w.mean, w.m2);
+  wp[1] = make_double2(w.var, w.sd);
+  wp[2] = make_double2(w.zmax, w.zmin);
+  d.welford_n[e] = w.count;
+  reinterpret_cast<double2*>(d.est_mm)[e] = make_double2(emx, emn);
+  d.tick[e] = tick + 1;
+  if (fl) atomicOr(&d.flags[e], fl);
+}
+
+// --------------------------------------------------------------------------------------------
+// K5: masked reset.  One thread per env regenerates the scenario (stream 1) and clears the
+// scalar state; k_zero_maps clears the three persistent maps with 16-byte stores.
+__device__ __forceinline__ int draw_int(Draws& dr, int n) {
+  int v = (int)floor(__dmul_rn(dr.next(), (double)n));
+  return v >= n ? n - 1 : v;
+}
+
+__global__ void __launch_bounds__(128)
+k_reset_state(const EnvDev d, const uint8_t* __restrict__ mask, int32_t* __restrict__ obs_xy) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.E) return;
+  const int A = d.A, G = d.G;
+  const bool doit = mask == nullptr || mask[e] != 0;
+  int2* agent = reinterpret_cast<int2*>(d.agent_xy) + (size_t)e * A;
+  if (!doit) {
+    if (obs_xy)
+      for (int a = 0; a < A; ++a) reinterpret_cast<int2*>(obs_xy)[(size_t)e * A + a] = agent[a];
+    return;
+  }
+  const int episode = d.episode[e] + 1;
+  d.episode[e] = episode;
+  int2* start = reinterpret_cast<int2*>(d.start_xy) + (size_t)e * A;
+  int2 src;
+  if (!d.fixed) {
+    Draws dr;
+    dr.init(d.seed, d.gid_base + e, STREAM_SCENARIO, 0, 0, episode);
+    src.x = draw_int(dr, G);
+    src.y = draw_int(dr, G);
+    d.src_int[e] = __dadd_rn(d.src_lo, __dmul_rn(dr.next(), d.src_span));
+    d.bkg[e] = __dadd_rn(d.bkg_lo, __dmul_rn(dr.next(), d.bkg_span));
+    reinterpret_cast<int2*>(d.src_xy)[e] = src;
+    int2 st[RT_MAX_AGENTS];
+    for (int a = 0; a < A; ++a) {
+      bool ok = false;
+      int2 p = make_int2(0, 0);
+      for (int t = 0; t < 8 && !ok; ++t) {
+        p.x = draw_int(dr, G);
+        p.y = draw_int(dr, G);
+        ok = abs(p.x - src.x) + abs(p.y - src.y) > 1;
+      }
+      if (!ok) p = make_int2((src.x + G / 2) % G, (src.y + G / 2) % G);
+      st[a] = p;
+      start[a] = p;
+    }
+    float4* edges = reinterpret_cast<float4*>(d.edges) + (size_t)e * RT_MAX_EDGES;
+    for (int j = 0; j < RT_MAX_EDGES; ++j) edges[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int np = d.poly_min;
+    if (d.poly_max > d.poly_min) np += draw_int(dr, d.poly_max - d.poly_min + 1);
+    d.n_poly[e] = np;
+    for (int p = 0; p < np; ++p) {
+      for (int t = 0; t < 8; ++t) {
+        int w = d.rect_min + draw_int(dr, d.rect_max - d.rect_min + 1);
+        int h = d.rect_min + draw_int(dr, d.rect_max - d.rect_min + 1);
+        w = min(w, G);
+        h = min(h, G);
+        const int x0 = draw_int(dr, G - w + 1);
+        const int y0 = draw_int(dr, G - h + 1);
+        bool bad = src.x >= x0 && src.x < x0 + w && src.y >= y0 && src.y < y0 + h;
+        for (int a = 0; a < A; ++a)
+          bad |= st[a].x >= x0 && st[a].x < x0 + w && st[a].y >= y0 && st[a].y < y0 + h;
+        if (bad) continue;
+        const float X0 = (float)x0, Y0 = (float)y0, X1 = (float)(x0 + w), Y1 = (float)(y0 + h);
+        edges[4 * p + 0] = make_float4(X0, Y0, X1, Y0);
+        edges[4 * p + 1] = make_float4(X1, Y0, X1, Y1);
+        edges[4 * p + 2] = make_float4(X1, Y1, X0, Y1);
+        edges[4 * p + 3] = make_float4(X0, Y1, X0, Y0);
+        break;
+      }
+    }
+  } else {
+    src = reinterpret_cast<const int2*>(d.src_xy)[e];
+  }
+  for (int a = 0; a < A; ++a) {
+    const size_t ia = (size_t)e * A + a;
+    const int2 p = start[a];
+    agent[a] = p;  // simple_gridworld.py:120
+    d.prev_dist[ia] = abs(p.x - src.x) + abs(p.y - src.y);  // :121
+    if (obs_xy) reinterpret_cast<int2*>(obs_xy)[ia] = p;
+    d.last_count[ia] = 0;
+    d.last_los[ia] = 0;
+    d.last_lambda[ia] = 0.0;
+    d.last_est[ia] = 0.0;
+    d.last_z[ia] = 0.0;
+    d.last_value[ia] = 0.0;
+  }
+  d.tick[e] = 0;
+  double2* wp = reinterpret_cast<double2*>(d.welford + (size_t)e * 6);
+  wp[0] = make_double2(0.0, 0.0);  // standardize.py:36-44
+  wp[1] = make_double2(0.0, 1.0);
+  wp[2] = make_double2(0.0, 0.0);
+  d.welford_n[e] = 0;
+  reinterpret_cast<double2*>(d.est_mm)[e] = make_double2(0.0, 0.0);  // estimator.py:25-29
+}
+
+// visit (2 B) + head (2 B) + intensity (4 B) per cell; 16-byte stores, one CTA-row per env.
+__global__ void __launch_bounds__(256)
+k_zero_maps(const EnvDev d, const uint8_t* __restrict__ mask) {
+  const int e = blockIdx.x;
+  if (mask != nullptr && mask[e] == 0) return;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  const size_t b16 = (size_t)d.cells * 2, b32 = (size_t)d.cells * 4;
+  unsigned char* v = reinterpret_cast<unsigned char*>(d.visit) + (size_t)e * b16;
+  unsigned char* h = reinterpret_cast<unsigned char*>(d.head) + (size_t)e * b16;
+  unsigned char* f = reinterpret_cast<unsigned char*>(d.inten) + (size_t)e * b32;
+  if ((d.cells & 7) == 0) {
+    for (size_t i = threadIdx.x * 16; i < b16; i += blockDim.x * 16) {
+      *reinterpret_cast<uint4*>(v + i) = z;
+      *reinterpret_cast<uint4*>(h + i) = z;
+    }
+    for (size_t i = threadIdx.x * 16; i < b32; i += blockDim.x * 16) *reinterpret_cast<uint4*>(f + i) = z;
+  } else {
+    for (int i = threadIdx.x; i < d.cells; i += blockDim.x) {
+      d.visit[(size_t)e * d.cells + i] = 0;
+      d.head[(size_t)e * d.cells + i] = 0;
+      d.inten[(size_t)e * d.cells + i] = 0.f;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// K3: rasterise.  Vector path (cells % 8 == 0): a thread owns 8 consecutive cells of one env —
+// one 16 B load of visit counts, two 16 B loads of intensities, six 16 B streaming stores
+// (3 channels x 32 B).  A warp therefore writes 3 x 1 KB fully coalesced per pass.
+__device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_f4(float* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+template <bool kLutInSmem>
+__global__ void __launch_bounds__(256)
+k_raster_vec(const EnvDev d, float* __restrict__ out, long long n_chunks) {
+  extern __shared__ float s_lut[];
+  if (kLutInSmem) {
+    for (int i = threadIdx.x; i <= d.cap; i += blockDim.x) s_lut[i] = d.lut[i];
+    __syncthreads();
+  }
+  const float* lut = kLutInSmem ? s_lut : d.lut;
+  const int cpe = d.cells >> 3;  // chunks per env
+  const int A = d.A, G = d.G;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += stride) {
+    const int e = (int)(c / cpe);
+    const int q = (int)(c - (long long)e * cpe);
+    const size_t cell0 = (size_t)e * d.cells + (size_t)q * 8;
+    const uint4 vv = ld_stream_u4(d.visit + cell0);
+    const uint4 i0 = ld_stream_u4(d.inten + cell0);
+    const uint4 i1 = ld_stream_u4(d.inten + cell0 + 4);
+    float loc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int2* agent = reinterpret_cast<const int2*>(d.agent_xy) + (size_t)e * A;
+    for (int a = 0; a < A; ++a) {
+      const int2 p = agent[a];
+      const int rel = p.y * G + p.x - q * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (rel == j) loc[j] = 1.0f;
+    }
+    float* o = out + (size_t)e * 3 * d.cells + (size_t)q * 8;
+    st_stream_f4(o, make_float4(loc[0], loc[1], loc[2], loc[3]));
+    st_stream_f4(o + 4, make_float4(loc[4], loc[5], loc[6], loc[7]));
+    o += d.cells;
+    st_stream_f4(o, make_float4(__uint_as_float(i0.x), __uint_as_float(i0.y), __uint_as_float(i0.z),
+                                __uint_as_float(i0.w)));
+    st_stream_f4(o + 4, make_float4(__uint_as_float(i1.x), __uint_as_float(i1.y), __uint_as_float(i1.z),
+                                    __uint_as_float(i1.w)));
+    o += d.cells;
+    st_stream_f4(o, make_float4(lut[vv.x & 0xffffu], lut[vv.x >> 16], lut[vv.y & 0xffffu], lut[vv.y >> 16]));
+    st_stream_f4(o + 4, make_float4(lut[vv.z & 0xffffu], lut[vv.z >> 16], lut[vv.w & 0xffffu], lut[vv.w >> 16]));
+  }
+}
+
+// Generic path for any grid side (the reference default size=10 has 100 cells): one cell per thread.
+__global__ void __launch_bounds__(256)
+k_raster_any(const EnvDev d, float* __restrict__ out, long long n_cells_total) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells_total; c += stride) {
+    const int e = (int)(c / d.cells);
+    const int cell = (int)(c - (long long)e * d.cells);
+    float loc = 0.f;
+    const int2* agent = reinterpret_cast<const int2*>(d.agent_xy) + (size_t)e * d.A;
+    for (int a = 0; a < d.A; ++a) {
+      const int2 p = agent[a];
+      if (p.y * d.G + p.x == cell) loc = 1.0f;
+    }
+    float* o = out + (size_t)e * 3 * d.cells + cell;
+    o[0] = loc;
+    o[d.cells] = d.inten[c];
+    o[2 * (size_t)d.cells] = d.lut[d.visit[c]];
+  }
+}
+
+}  // namespace rt

@@ -1,0 +1,30 @@
+// rt_host.h — host-side helpers shared by the translation units of librt_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/rt_b200.h"
+
+// Last CUDA failure seen by this library (for rt_status_string(RT_ERR_CUDA)).
+const char* rt_last_cuda_error();
+void rt_note_cuda_error(cudaError_t err, const char* what);
+
+#define RT_CUDA(call)                         \
+  do {                                        \
+    cudaError_t rt_e_ = (call);               \
+    if (rt_e_ != cudaSuccess) {               \
+      rt_note_cuda_error(rt_e_, #call);       \
+      return RT_ERR_CUDA;                     \
+    }                                         \
+  } while (0)
+
+#define RT_CUDA_OR(call, cleanup)             \
+  do {                                        \
+    cudaError_t rt_e_ = (call);               \
+    if (rt_e_ != cudaSuccess) {               \
+      rt_note_cuda_error(rt_e_, #call);       \
+      cleanup;                                \
+      return RT_ERR_CUDA;                     \
+    }                                         \
+  } while (0)
+
+#define RT_CUDA_LAUNCH_CHECK() RT_CUDA(cudaGetLastError())

@@ -1,0 +1,661 @@
+// rt_stats.cu — the src/math_utils interfaces as batched sm_100a kernels:
+//   rt_welford_*    per-stream WelfordsOnlineStandardization   (standardize.py:7-107)
+//   rt_moments_*    K4b: batch running moments, warp-shuffle Chan merges, NCCL-mergeable
+//   rt_normalize    Normalizer.normalize                        (normalize.py:25-55)
+//   rt_lognormalize BensLogNormalizer                           (normalize.py:79-115)
+//   rt_estimator_*  IntensityResamplingEstimator                (estimator.py:6-109)
+#include <math_constants.h>
+
+#include <new>
+#include <vector>
+
+#include "rt_device.cuh"
+#include "rt_host.h"
+
+using namespace rt;
+
+// ============================================================================================
+// Per-stream Welford: state double[n][6] = mean, M2, var, std, zmax, zmin; int32[n] count.
+struct rt_welford {
+  long long n = 0;
+  double* state = nullptr;
+  int32_t* count = nullptr;
+};
+
+namespace {
+
+__global__ void __launch_bounds__(256) k_welford_reset(double* __restrict__ st, int32_t* __restrict__ cnt,
+                                                      long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double2* p = reinterpret_cast<double2*>(st + i * 6);
+  p[0] = make_double2(0.0, 0.0);
+  p[1] = make_double2(0.0, 1.0);
+  p[2] = make_double2(0.0, 0.0);
+  cnt[i] = 0;
+}
+
+__device__ __forceinline__ WelfordState load_w(const double* st, const int32_t* cnt, long long i) {
+  const double2* p = reinterpret_cast<const double2*>(st + i * 6);
+  const double2 a = p[0], b = p[1], c = p[2];
+  WelfordState w;
+  w.mean = a.x; w.m2 = a.y; w.var = b.x; w.sd = b.y; w.zmax = c.x; w.zmin = c.y;
+  w.count = cnt[i];
+  return w;
+}
+
+__global__ void __launch_bounds__(256)
+k_welford_update(double* __restrict__ st, int32_t* __restrict__ cnt, const double* __restrict__ reading,
+                 int32_t* __restrict__ err, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double r = reading[i];
+  if (!(r >= 0.0)) {  // standardize.py:63
+    if (err) err[i] = RT_ERR_ASSERT;
+    return;
+  }
+  WelfordState w = load_w(st, cnt, i);
+  welford_update(w, r);
+  double2* p = reinterpret_cast<double2*>(st + i * 6);
+  p[0] = make_double2(w.mean, w.m2);
+  p[1] = make_double2(w.var, w.sd);
+  p[2] = make_double2(w.zmax, w.zmin);
+  cnt[i] = w.count;
+  if (err) err[i] = RT_OK;
+}
+
+__global__ void __launch_bounds__(256)
+k_welford_standardize(const double* __restrict__ st, const double* __restrict__ reading,
+                      double* __restrict__ z, int32_t* __restrict__ err, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double r = reading[i];
+  if (!(r >= 0.0)) {  // standardize.py:92
+    if (err) err[i] = RT_ERR_ASSERT;
+    z[i] = CUDART_NAN;
+    return;
+  }
+  const double2* p = reinterpret_cast<const double2*>(st + i * 6);
+  const double mean = p[0].x, sd = p[1].y;
+  z[i] = __ddiv_rn(__dsub_rn(r, mean), sd);
+  if (err) err[i] = RT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rt_welford_create(int64_t n, rt_welford** out) {
+  if (n < 1 || !out) return RT_ERR_BAD_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    rt_note_cuda_error(cudaGetLastError(), "cudaGetDeviceCount");
+    return RT_ERR_CUDA;
+  }
+  rt_welford* w = new (std::nothrow) rt_welford();
+  if (!w) return RT_ERR_NOMEM;
+  w->n = n;
+  if (cudaMalloc((void**)&w->state, (size_t)n * 48) != cudaSuccess ||
+      cudaMalloc((void**)&w->count, (size_t)n * 4) != cudaSuccess) {
+    rt_note_cuda_error(cudaGetLastError(), "cudaMalloc(welford)");
+    rt_welford_destroy(w);
+    return RT_ERR_NOMEM;
+  }
+  const int rc = rt_welford_reset(w, nullptr);
+  if (rc != RT_OK) {
+    rt_welford_destroy(w);
+    return rc;
+  }
+  RT_CUDA(cudaDeviceSynchronize());
+  *out = w;
+  return RT_OK;
+}
+
+int rt_welford_destroy(rt_welford* w) {
+  if (!w) return RT_OK;
+  if (w->state) cudaFree(w->state);
+  if (w->count) cudaFree(w->count);
+  delete w;
+  return RT_OK;
+}
+
+int rt_welford_reset(rt_welford* w, void* stream) {
+  if (!w) return RT_ERR_BAD_ARG;
+  k_welford_reset<<<(unsigned)((w->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w->state, w->count, w->n);
+  RT_CUDA_LAUNCH_CHECK();
+  return RT_OK;
+}
+
+int rt_welford_update(rt_welford* w, const double* reading_dev, int32_t* err_dev, void* stream) {
+  if (!w || !reading_dev) return RT_ERR_BAD_ARG;
+  k_welford_update<<<(unsigned)((w->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      w->state, w->count, reading_dev, err_dev, w->n);
+  RT_CUDA_LAUNCH_CHECK();
+  return RT_OK;
+}
+
+int rt_welford_standardize(rt_welford* w, const double* reading_dev, double* z_dev, int32_t* err_dev,
+                           void* stream) {
+  if (!w || !reading_dev || !z_dev) return RT_ERR_BAD_ARG;
+  k_welford_standardize<<<(unsigned)((w->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      w->state, reading_dev, z_dev, err_dev, w->n);
+  RT_CUDA_LAUNCH_CHECK();
+  return RT_OK;
+}
+
+int rt_welford_buffers(rt_welford* w, void** state_dev, void** count_dev) {
+  if (!w) return RT_ERR_BAD_ARG;
+  if (state_dev) *state_dev = w->state;
+  if (count_dev) *count_dev = w->count;
+  return RT_OK;
+}
+
+}  // extern "C"
+
+// ============================================================================================
+// K4b: batch running moments.  state double[3] = {count, mean, M2}.
+//
+// Pass 1 (k_moments_partial): each thread folds 16-byte vectors of fp32 readings into a private
+// (n, mean, M2) — four values at a time: exact two-pass moments of the quad in registers, then one
+// Chan merge — so there is one fp64 divide per 4 readings, not per reading.  Warps combine with
+// five shuffle-down Chan merges, warps of a CTA through shared memory, and each CTA writes one
+// partial triple.  Pass 2 (k_moments_final, one warp) merges the CTA partials in index order and
+// folds the result into the running state.  Every merge order is fixed by (n, grid), so the result
+// is deterministic run to run; it differs from the sequential recurrence only by rounding.
+struct rt_moments {
+  double* state = nullptr;     // [3]
+  double* partials = nullptr;  // [max_blocks][3]
+  int max_blocks = 0;
+};
+
+namespace {
+
+struct Mom {
+  double n, mean, m2;
+};
+
+__device__ __forceinline__ Mom chan(const Mom a, const Mom b) {
+  if (b.n == 0.0) return a;
+  if (a.n == 0.0) return b;
+  Mom r;
+  r.n = a.n + b.n;
+  const double delta = b.mean - a.mean;
+  const double f = b.n / r.n;
+  r.mean = a.mean + delta * f;
+  r.m2 = a.m2 + b.m2 + delta * delta * (a.n * f);
+  return r;
+}
+
+__device__ __forceinline__ Mom warp_merge(Mom m) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    Mom o;
+    o.n = __shfl_down_sync(0xffffffffu, m.n, off);
+    o.mean = __shfl_down_sync(0xffffffffu, m.mean, off);
+    o.m2 = __shfl_down_sync(0xffffffffu, m.m2, off);
+    m = chan(m, o);
+  }
+  return m;
+}
+
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ void fold_quad(Mom& acc, const float4 v) {
+  const double a = (double)v.x, b = (double)v.y, c = (double)v.z, d = (double)v.w;
+  const double mean = ((a + b) + (c + d)) * 0.25;
+  const double da = a - mean, db = b - mean, dc = c - mean, dd = d - mean;
+  Mom q;
+  q.n = 4.0;
+  q.mean = mean;
+  q.m2 = (da * da + db * db) + (dc * dc + dd * dd);
+  acc = chan(acc, q);
+}
+
+constexpr int kMomThreads = 256;
+constexpr int kMomUnroll = 4;  // 16-byte loads in flight per thread
+
+__global__ void __launch_bounds__(kMomThreads)
+k_moments_partial(const float* __restrict__ x, long long n, double* __restrict__ partials) {
+  __shared__ Mom s_w[kMomThreads / 32];
+  Mom acc = {0.0, 0.0, 0.0};
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * kMomThreads;
+  long long i = (long long)blockIdx.x * kMomThreads + threadIdx.x;
+  for (; i + (kMomUnroll - 1) * stride < n4; i += kMomUnroll * stride) {
+    float4 v[kMomUnroll];
+#pragma unroll
+    for (int u = 0; u < kMomUnroll; ++u) v[u] = ld_stream_f4(x + 4 * (i + u * stride));
+#pragma unroll
+    for (int u = 0; u < kMomUnroll; ++u) fold_quad(acc, v[u]);
+  }
+  for (; i < n4; i += stride) fold_quad(acc, ld_stream_f4(x + 4 * i));
+  // tail (n % 4 readings): one Welford step each, by the first threads of block 0
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n & 3)) {
+    Mom q = {1.0, (double)x[(n4 << 2) + threadIdx.x], 0.0};
+    acc = chan(acc, q);
+  }
+  acc = warp_merge(acc);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    Mom m = threadIdx.x < kMomThreads / 32 ? s_w[threadIdx.x] : Mom{0.0, 0.0, 0.0};
+    m = warp_merge(m);
+    if (threadIdx.x == 0) {
+      partials[3 * blockIdx.x + 0] = m.n;
+      partials[3 * blockIdx.x + 1] = m.mean;
+      partials[3 * blockIdx.x + 2] = m.m2;
+    }
+  }
+}
+
+// one warp: lane l merges partials l, l+32, ... in order, then a shuffle tree, then the state
+__global__ void k_moments_final(const double* __restrict__ partials, int n_partials, double* __restrict__ state,
+                                int replace) {
+  Mom m = {0.0, 0.0, 0.0};
+  for (int i = threadIdx.x; i < n_partials; i += 32) {
+    Mom p = {partials[3 * i], partials[3 * i + 1], partials[3 * i + 2]};
+    m = chan(m, p);
+  }
+  m = warp_merge(m);
+  if (threadIdx.x == 0) {
+    Mom s = {state[0], state[1], state[2]};
+    if (replace) s = Mom{0.0, 0.0, 0.0};
+    s = chan(s, m);
+    state[0] = s.n;
+    state[1] = s.mean;
+    state[2] = s.m2;
+  }
+}
+
+// rank-ordered merge of gathered triples (strictly sequential: bit-identical on every rank)
+__global__ void k_moments_merge(const double* __restrict__ gathered, int n_ranks, double* __restrict__ state) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Mom s = {0.0, 0.0, 0.0};
+  for (int r = 0; r < n_ranks; ++r) {
+    Mom p = {gathered[3 * r], gathered[3 * r + 1], gathered[3 * r + 2]};
+    s = chan(s, p);
+  }
+  state[0] = s.n;
+  state[1] = s.mean;
+  state[2] = s.m2;
+}
+
+__global__ void __launch_bounds__(256)
+k_moments_standardize(const double* __restrict__ state, const float* __restrict__ x, float* __restrict__ out,
+                      long long n) {
+  const double cnt = state[0], mean = state[1], m2 = state[2];
+  double sd = 1.0;
+  if (cnt >= 2.0) {
+    const double s = sqrt(m2 / (cnt - 1.0));
+    sd = s > 1.0 ? s : 1.0;  // standardize.py:74
+  }
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = ld_stream_f4(x + 4 * i);
+    float4 o;
+    o.x = (float)(((double)v.x - mean) / sd);
+    o.y = (float)(((double)v.y - mean) / sd);
+    o.z = (float)(((double)v.z - mean) / sd);
+    o.w = (float)(((double)v.w - mean) / sd);
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(out + 4 * i), "f"(o.x), "f"(o.y), "f"(o.z),
+                 "f"(o.w)
+                 : "memory");
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n & 3)) {
+    const long long j = (n4 << 2) + threadIdx.x;
+    out[j] = (float)(((double)x[j] - mean) / sd);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int rt_moments_create(rt_moments** out) {
+  if (!out) return RT_ERR_BAD_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    rt_note_cuda_error(cudaGetLastError(), "cudaGetDeviceCount");
+    return RT_ERR_CUDA;
+  }
+  rt_moments* m = new (std::nothrow) rt_moments();
+  if (!m) return RT_ERR_NOMEM;
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  m->max_blocks = n_sm * 8;  // 8 resident 256-thread CTAs per SM: one full wave
+  if (cudaMalloc((void**)&m->state, 3 * sizeof(double)) != cudaSuccess ||
+      cudaMalloc((void**)&m->partials, (size_t)m->max_blocks * 3 * sizeof(double)) != cudaSuccess) {
+    rt_note_cuda_error(cudaGetLastError(), "cudaMalloc(moments)");
+    rt_moments_destroy(m);
+    return RT_ERR_NOMEM;
+  }
+  RT_CUDA(cudaMemset(m->state, 0, 3 * sizeof(double)));
+  *out = m;
+  return RT_OK;
+}
+
+int rt_moments_destroy(rt_moments* m) {
+  if (!m) return RT_OK;
+  if (m->state) cudaFree(m->state);
+  if (m->partials) cudaFree(m->partials);
+  delete m;
+  return RT_OK;
+}
+
+int rt_moments_reset(rt_moments* m, void* stream) {
+  if (!m) return RT_ERR_BAD_ARG;
+  RT_CUDA(cudaMemsetAsync(m->state, 0, 3 * sizeof(double), (cudaStream_t)stream));
+  return RT_OK;
+}
+
+int rt_moments_update(rt_moments* m, const float* x_dev, int64_t n, void* stream) {
+  if (!m || !x_dev || n < 0) return RT_ERR_BAD_ARG;
+  if (((uintptr_t)x_dev & 15) != 0) return RT_ERR_BAD_ARG;  // 16-byte vector loads
+  if (n == 0) return RT_OK;
+  long long blocks = ((n >> 2) + kMomThreads * kMomUnroll - 1) / (kMomThreads * kMomUnroll);
+  if (blocks < 1) blocks = 1;
+  if (blocks > m->max_blocks) blocks = m->max_blocks;
+  k_moments_partial<<<(unsigned)blocks, kMomThreads, 0, (cudaStream_t)stream>>>(x_dev, n, m->partials);
+  k_moments_final<<<1, 32, 0, (cudaStream_t)stream>>>(m->partials, (int)blocks, m->state, 0);
+  RT_CUDA_LAUNCH_CHECK();
+  return RT_OK;
+}
+
+int rt_moments_standardize(rt_moments* m, const float* x_dev, float* out_dev, int64_t n, void* stream) {
+  if (!m || !x_dev || !out_dev || n < 0) return RT_ERR_BAD_ARG;
+  if ((((uintptr_t)x_dev | (uintptr_t)out_dev) & 15) != 0) return RT_ERR_BAD_ARG;
+  if (n == 0) return RT_OK;
+  long long blocks = ((n >> 2) + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > (long long)m->max_blocks * 4) blocks = (long long)m->max_blocks * 4;
+  k_moments_standardize<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(m->state, x_dev, out_dev, n);
+  RT_CUDA_LAUNCH_CHECK();
+  return RT_OK;
+}
+
+int rt_moments_state(rt_moments* m, void** state_dev) {
+  if (!m || !state_dev) return RT_ERR_BAD_ARG;
+  *state_dev = m->state;
+  return RT_OK;
+}
+
+int rt_moments_merge(rt_moments* m, const double* gathered_dev, int32_t n_ranks, void* stream) {
+  if (!m || !gathered_dev || n_ranks < 1) return RT_ERR_BAD_ARG;
+  k_moments_merge<<<1, 32, 0, (cudaStream_t)stream>>>(gathered_dev, n_ranks, m->state);
+  RT_CUDA_LAUNCH_CHECK();
+  return RT_OK;
+}
+
+}  // extern "C"
+
+// ============================================================================================
+// Elementwise normalisers.
+namespace {
+
+__global__ void __launch_bounds__(256)
+k_normalize(const double* __restrict__ cur, const double* __restrict__ mx, const double* __restrict__ mn,
+            double* __restrict__ out, int32_t* __restrict__ err, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double r;
+  const bool ok = normalize_minmax(cur[i], mx[i], mn != nullptr, mn ? mn[i] : 0.0, r);
+  out[i] = r;
+  if (err) err[i] = ok ? RT_OK : RT_ERR_ASSERT;
+}
+
+// normalize.py:110: log(step + v, max) * 1 / log(step * max, max), math.log(x, b) = ln x / ln b
+__global__ void __launch_bounds__(256)
+k_lognormalize(const double* __restrict__ cur, double mx, int step, double* __restrict__ out,
+               int32_t* __restrict__ err, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = cur[i];
+  double r = CUDART_NAN;
+  int rc = RT_ERR_ASSERT;
+  if (v >= 0.0 && mx > 0.0 && step > 0 && mx != 1.0) {  // normalize.py:90 (max == 1: ZeroDivisionError)
+    const double lb = dlog(mx);
+    const double num = __ddiv_rn(dlog(__dadd_rn((double)step, v)), lb);
+    const double den = __ddiv_rn(dlog(__dmul_rn((double)step, mx)), lb);
+    const double q = __ddiv_rn(__dmul_rn(num, 1.0), den);
+    if (q >= 0.0 && q <= 1.0) {  // :111-113
+      r = q;
+      rc = RT_OK;
+    }
+  }
+  out[i] = r;
+  if (err) err[i] = rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rt_normalize(const double* current_dev, const double* max_dev, const double* min_dev, double* out_dev,
+                 int32_t* err_dev, int64_t n, void* stream) {
+  if (!current_dev || !max_dev || !out_dev || n < 0) return RT_ERR_BAD_ARG;
+  if (n == 0) return RT_OK;
+  k_normalize<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(current_dev, max_dev, min_dev,
+                                                                          out_dev, err_dev, n);
+  RT_CUDA_LAUNCH_CHECK();
+  return RT_OK;
+}
+
+int rt_lognormalize(const double* current_dev, double max, int32_t step_size, double* out_dev, int32_t* err_dev,
+                    int64_t n, void* stream) {
+  if (!current_dev || !out_dev || n < 0) return RT_ERR_BAD_ARG;
+  if (n == 0) return RT_OK;
+  k_lognormalize<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(current_dev, max, step_size,
+                                                                             out_dev, err_dev, n);
+  RT_CUDA_LAUNCH_CHECK();
+  return RT_OK;
+}
+
+}  // extern "C"
+
+// ============================================================================================
+// Stand-alone IntensityResamplingEstimator: n estimators, `n_keys` key slots, `capacity` readings
+// each.  Readings are nodes {value, key, next-larger-of-same-key}; per key the nodes form a list
+// sorted by value (median = walk to the middle), and the node array itself is insertion order
+// (get_buffer = filtered scan).
+struct rt_estimator {
+  long long n = 0;
+  int n_keys = 0, capacity = 0;
+  double* value = nullptr;   // [n][capacity]
+  int32_t* key = nullptr;    // [n][capacity]
+  int32_t* next = nullptr;   // [n][capacity]  +1 encoded
+  int32_t* head = nullptr;   // [n][n_keys]    +1 encoded, smallest value of the key
+  int32_t* klen = nullptr;   // [n][n_keys]    readings per key
+  int32_t* used = nullptr;   // [n]
+  double* maxmin = nullptr;  // [n][2]
+};
+
+namespace {
+
+__device__ __forceinline__ double est_median(const rt_estimator& s, long long i, int key) {
+  const int n = s.klen[i * s.n_keys + key];
+  const int k1 = (n - 1) >> 1, k2 = n >> 1;
+  int cur = s.head[i * s.n_keys + key];
+  double m1 = 0.0, m2 = 0.0;
+  for (int j = 0; j <= k2; ++j) {
+    const double v = s.value[i * s.capacity + (cur - 1)];
+    if (j == k1) m1 = v;
+    if (j == k2) m2 = v;
+    cur = s.next[i * s.capacity + (cur - 1)];
+  }
+  return (n & 1) ? m2 : __ddiv_rn(__dadd_rn(m1, m2), 2.0);  // statistics.median
+}
+
+__global__ void __launch_bounds__(128)
+k_est_update(const rt_estimator s, const int32_t* __restrict__ key, const double* __restrict__ value,
+             double* __restrict__ est_out, int32_t* __restrict__ err) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s.n) return;
+  const int k = key[i];
+  const int idx = s.used[i];
+  if (k < 0 || k >= s.n_keys || idx >= s.capacity) {
+    if (err) err[i] = RT_ERR_BAD_ARG;
+    return;
+  }
+  const double v = value[i];
+  // sorted insert (after equal values)
+  int pred = 0, cur = s.head[i * s.n_keys + k];
+  while (cur != 0 && !(s.value[i * s.capacity + (cur - 1)] > v)) {
+    pred = cur;
+    cur = s.next[i * s.capacity + (cur - 1)];
+  }
+  s.value[i * s.capacity + idx] = v;
+  s.key[i * s.capacity + idx] = k;
+  s.next[i * s.capacity + idx] = cur;
+  if (pred == 0)
+    s.head[i * s.n_keys + k] = idx + 1;
+  else
+    s.next[i * s.capacity + (pred - 1)] = idx + 1;
+  s.klen[i * s.n_keys + k] += 1;
+  s.used[i] = idx + 1;
+  const double est = est_median(s, i, k);  // estimator.py:44
+  double mx = s.maxmin[2 * i], mn = s.maxmin[2 * i + 1];
+  est_maxmin(est, mx, mn);  // :45-48
+  s.maxmin[2 * i] = mx;
+  s.maxmin[2 * i + 1] = mn;
+  if (est_out) est_out[i] = est;
+  if (err) err[i] = RT_OK;
+}
+
+__global__ void __launch_bounds__(128)
+k_est_estimate(const rt_estimator s, const int32_t* __restrict__ key, double* __restrict__ est_out,
+               int32_t* __restrict__ err) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s.n) return;
+  const int k = key[i];
+  if (k < 0 || k >= s.n_keys || s.klen[i * s.n_keys + k] == 0) {  // estimator.py:68-69
+    est_out[i] = CUDART_NAN;
+    if (err) err[i] = RT_ERR_KEY;
+    return;
+  }
+  est_out[i] = est_median(s, i, k);
+  if (err) err[i] = RT_OK;
+}
+
+__global__ void __launch_bounds__(128)
+k_est_buffer(const rt_estimator s, const int32_t* __restrict__ key, double* __restrict__ out,
+             int32_t* __restrict__ n_out, int max_out, int32_t* __restrict__ err) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s.n) return;
+  const int k = key[i];
+  if (k < 0 || k >= s.n_keys || s.klen[i * s.n_keys + k] == 0) {  // estimator.py:57-58
+    n_out[i] = 0;
+    if (err) err[i] = RT_ERR_KEY;
+    return;
+  }
+  int m = 0;
+  const int used = s.used[i];
+  for (int j = 0; j < used; ++j)
+    if (s.key[i * s.capacity + j] == k) {
+      if (m < max_out) out[i * max_out + m] = s.value[i * s.capacity + j];
+      ++m;
+    }
+  n_out[i] = m;
+  if (err) err[i] = RT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rt_estimator_create(int64_t n, int32_t n_keys, int32_t capacity, rt_estimator** out) {
+  if (n < 1 || n_keys < 1 || capacity < 1 || !out) return RT_ERR_BAD_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    rt_note_cuda_error(cudaGetLastError(), "cudaGetDeviceCount");
+    return RT_ERR_CUDA;
+  }
+  rt_estimator* s = new (std::nothrow) rt_estimator();
+  if (!s) return RT_ERR_NOMEM;
+  s->n = n;
+  s->n_keys = n_keys;
+  s->capacity = capacity;
+  const size_t nc = (size_t)n * capacity, nk = (size_t)n * n_keys;
+  bool ok = cudaMalloc((void**)&s->value, nc * 8) == cudaSuccess &&
+            cudaMalloc((void**)&s->key, nc * 4) == cudaSuccess &&
+            cudaMalloc((void**)&s->next, nc * 4) == cudaSuccess &&
+            cudaMalloc((void**)&s->head, nk * 4) == cudaSuccess &&
+            cudaMalloc((void**)&s->klen, nk * 4) == cudaSuccess &&
+            cudaMalloc((void**)&s->used, (size_t)n * 4) == cudaSuccess &&
+            cudaMalloc((void**)&s->maxmin, (size_t)n * 16) == cudaSuccess;
+  if (!ok) {
+    rt_note_cuda_error(cudaGetLastError(), "cudaMalloc(estimator)");
+    rt_estimator_destroy(s);
+    return RT_ERR_NOMEM;
+  }
+  const int rc = rt_estimator_reset(s, nullptr);
+  if (rc != RT_OK) {
+    rt_estimator_destroy(s);
+    return rc;
+  }
+  RT_CUDA(cudaDeviceSynchronize());
+  *out = s;
+  return RT_OK;
+}
+
+int rt_estimator_destroy(rt_estimator* s) {
+  if (!s) return RT_OK;
+  void* ptrs[] = {s->value, s->key, s->next, s->head, s->klen, s->used, s->maxmin};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete s;
+  return RT_OK;
+}
+
+int rt_estimator_reset(rt_estimator* s, void* stream) {  // estimator.py:25-29
+  if (!s) return RT_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nk = (size_t)s->n * s->n_keys;
+  RT_CUDA(cudaMemsetAsync(s->head, 0, nk * 4, st));
+  RT_CUDA(cudaMemsetAsync(s->klen, 0, nk * 4, st));
+  RT_CUDA(cudaMemsetAsync(s->used, 0, (size_t)s->n * 4, st));
+  RT_CUDA(cudaMemsetAsync(s->maxmin, 0, (size_t)s->n * 16, st));
+  return RT_OK;
+}
+
+int rt_estimator_update(rt_estimator* s, const int32_t* key_dev, const double* value_dev, double* est_dev,
+                        int32_t* err_dev, void* stream) {
+  if (!s || !key_dev || !value_dev) return RT_ERR_BAD_ARG;
+  k_est_update<<<(unsigned)((s->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*s, key_dev, value_dev,
+                                                                              est_dev, err_dev);
+  RT_CUDA_LAUNCH_CHECK();
+  return RT_OK;
+}
+
+int rt_estimator_estimate(rt_estimator* s, const int32_t* key_dev, double* est_dev, int32_t* err_dev,
+                          void* stream) {
+  if (!s || !key_dev || !est_dev) return RT_ERR_BAD_ARG;
+  k_est_estimate<<<(unsigned)((s->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*s, key_dev, est_dev,
+                                                                                err_dev);
+  RT_CUDA_LAUNCH_CHECK();
+  return RT_OK;
+}
+
+int rt_estimator_buffer(rt_estimator* s, const int32_t* key_dev, double* out_dev, int32_t* n_out_dev,
+                        int32_t max_out, int32_t* err_dev, void* stream) {
+  if (!s || !key_dev || !out_dev || !n_out_dev || max_out < 1) return RT_ERR_BAD_ARG;
+  k_est_buffer<<<(unsigned)((s->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*s, key_dev, out_dev,
+                                                                              n_out_dev, max_out, err_dev);
+  RT_CUDA_LAUNCH_CHECK();
+  return RT_OK;
+}
+
+int rt_estimator_maxmin(rt_estimator* s, void** maxmin_dev) {
+  if (!s || !maxmin_dev) return RT_ERR_BAD_ARG;
+  *maxmin_dev = s->maxmin;
+  return RT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,263 @@
+"""Batched radiation-search environment on one B200 — the Python face of rt_env_* (include/rt_b200.h).
+
+Mirrors the Gymnasium protocol of the reference env (src/envs/simple_gridworld.py:114-167):
+``reset(seed=None, options=None) -> (obs, info)`` and
+``step(actions) -> (obs, reward, terminated, truncated, info)``, with a leading ``[E, A]`` on everything.
+
+Two ways to call it:
+  * device path — ``actions`` is a CUDA int32 tensor: kernels are enqueued on torch's current stream and
+    CUDA tensors come back; nothing synchronises.
+  * host path — ``actions`` is a NumPy array / CPU tensor: the C ABI copies it up, steps, copies
+    obs / reward / done back (pinned) and returns NumPy arrays.  The heat-maps stay on the device: they
+    are written straight into ``obs_maps``, the CNN's input tensor.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import asdict, dataclass
+from typing import Any, Dict, Optional, Tuple
+
+import numpy as np
+
+from .. import _lib
+
+
+@dataclass
+class RadSearchConfig:
+    """Field-for-field rt_env_cfg (include/rt_b200.h)."""
+    n_envs: int = 1
+    n_agents: int = 1
+    grid: int = 32
+    max_steps: int = 120
+    poly_min: int = 0
+    poly_max: int = 0
+    rect_min: int = 2
+    rect_max: int = 6
+    lognorm_step: int = 2
+    fixed_scenario: int = 0
+    env_id_base: int = 0
+    seed: int = 0
+    cell_pitch_cm: float = 100.0
+    min_dist_cm: float = 50.0
+    transmission: float = 0.0
+    src_lo: float = 1e6
+    src_hi: float = 1e7
+    bkg_lo: float = 10.0
+    bkg_hi: float = 51.0
+
+    def to_c(self) -> _lib.EnvCfg:
+        return _lib.EnvCfg(**asdict(self))
+
+
+_BUF_SPEC = {
+    # name: (torch dtype name, shape lambda(E, A, cells, cap))
+    "AGENT_XY": ("int32", lambda E, A, c, cap: (E, A, 2)),
+    "PREV_DIST": ("int32", lambda E, A, c, cap: (E, A)),
+    "START_XY": ("int32", lambda E, A, c, cap: (E, A, 2)),
+    "SRC_XY": ("int32", lambda E, A, c, cap: (E, 2)),
+    "SRC_INT": ("float64", lambda E, A, c, cap: (E,)),
+    "BKG": ("float64", lambda E, A, c, cap: (E,)),
+    "N_POLY": ("int32", lambda E, A, c, cap: (E,)),
+    "EDGES": ("float32", lambda E, A, c, cap: (E, 20, 4)),
+    "TICK": ("int32", lambda E, A, c, cap: (E,)),
+    "EPISODE": ("int32", lambda E, A, c, cap: (E,)),
+    "VISIT": ("uint16", lambda E, A, c, cap: (E, c)),
+    "INTENSITY": ("float32", lambda E, A, c, cap: (E, c)),
+    "HEAD": ("uint16", lambda E, A, c, cap: (E, c)),
+    "LOG": ("int32", lambda E, A, c, cap: (cap, E, 2)),
+    "WELFORD": ("float64", lambda E, A, c, cap: (E, 6)),
+    "WELFORD_N": ("int32", lambda E, A, c, cap: (E,)),
+    "EST_MAXMIN": ("float64", lambda E, A, c, cap: (E, 2)),
+    "FLAGS": ("int32", lambda E, A, c, cap: (E,)),
+    "LAST_COUNT": ("int32", lambda E, A, c, cap: (E, A)),
+    "LAST_LOS": ("uint8", lambda E, A, c, cap: (E, A)),
+    "LAST_LAMBDA": ("float64", lambda E, A, c, cap: (E, A)),
+    "LAST_EST": ("float64", lambda E, A, c, cap: (E, A)),
+    "LAST_Z": ("float64", lambda E, A, c, cap: (E, A)),
+    "LAST_VALUE": ("float64", lambda E, A, c, cap: (E, A)),
+    "VISIT_LUT": ("float32", lambda E, A, c, cap: (cap + 1,)),
+}
+_ITEMSIZE = {"int32": 4, "float64": 8, "float32": 4, "uint16": 2, "uint8": 1}
+
+
+class BatchedRadSearchEnv:
+    """E independent radiation-search envs x A agents, resident on one GPU."""
+
+    metadata = {"render_modes": [], "render_fps": 4}
+
+    def __init__(self, cfg: Optional[RadSearchConfig] = None, device: Optional[int] = None,
+                 alloc_maps: bool = True, **kw: Any) -> None:
+        torch = _lib.require_cuda()
+        self._torch = torch
+        self.cfg = cfg if cfg is not None else RadSearchConfig(**kw)
+        self.E, self.A, self.G = self.cfg.n_envs, self.cfg.n_agents, self.cfg.grid
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            c = self.cfg.to_c()
+            _lib.check(self._L.rt_env_create(C.byref(c), C.byref(self._h)), "rt_env_create")
+        E, A, G = self.E, self.A, self.G
+        dev = self.device
+        # caller-visible outputs (device).  obs_maps is the CNN input tensor; pass alloc_maps=False
+        # and hand your own tensor to step(out_maps=...) to write into a rollout slot directly.
+        self.obs_xy = torch.zeros((E, A, 2), dtype=torch.int32, device=dev)
+        self.reward = torch.zeros((E, A), dtype=torch.int32, device=dev)
+        self.done = torch.zeros((E, A), dtype=torch.uint8, device=dev)
+        self.obs_maps = torch.zeros((E, 3, G, G), dtype=torch.float32, device=dev) if alloc_maps else None
+        # host-path outputs (pinned, so the C ABI copies straight into them)
+        self._h_xy = self._h_rw = self._h_dn = None
+        self._inj = None
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def _stream(self) -> int:
+        return self._torch.cuda.current_stream(self.device).cuda_stream
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.rt_env_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _host_bufs(self):
+        if self._h_xy is None:
+            t = self._torch
+            self._h_xy = t.zeros((self.E, self.A, 2), dtype=t.int32).pin_memory()
+            self._h_rw = t.zeros((self.E, self.A), dtype=t.int32).pin_memory()
+            self._h_dn = t.zeros((self.E, self.A), dtype=t.uint8).pin_memory()
+        return self._h_xy, self._h_rw, self._h_dn
+
+    def buffer(self, name: str):
+        """Zero-copy CUDA tensor view of one state array (rt_buf) — get_state / set_state."""
+        torch = self._torch
+        ptr, nbytes = C.c_void_p(), C.c_size_t()
+        _lib.check(self._L.rt_env_buffer(self._h, _lib.BUF[name], C.byref(ptr), C.byref(nbytes)), name)
+        dt, shp = _BUF_SPEC[name]
+        shape = shp(self.E, self.A, self.G * self.G, self.cfg.max_steps * self.A)
+        n = int(np.prod(shape))
+        assert n * _ITEMSIZE[dt] == nbytes.value, (name, shape, nbytes.value)
+
+        class _Arr:  # __cuda_array_interface__ carrier
+            pass
+
+        a = _Arr()
+        typestr = {"int32": "<i4", "float64": "<f8", "float32": "<f4", "uint16": "<u2", "uint8": "|u1"}[dt]
+        a.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr.value, False),
+                                      "version": 2, "strides": None}
+        return torch.as_tensor(a, device=self.device)
+
+    def state_dict(self) -> Dict[str, Any]:
+        """Snapshot of every persistent array (deterministic replay / checkpoint)."""
+        skip = {"VISIT_LUT"}
+        return {k: self.buffer(k).clone() for k in _BUF_SPEC if k not in skip}
+
+    def load_state_dict(self, sd: Dict[str, Any]) -> None:
+        for k, v in sd.items():
+            self.buffer(k).copy_(v)
+
+    def set_scenario(self, src_xy=None, src_int=None, bkg=None, start_xy=None, n_poly=None, edges=None) -> None:
+        E, A = self.E, self.A
+
+        def prep(a, dt, shape):
+            return None if a is None else np.ascontiguousarray(np.asarray(a, dtype=dt).reshape(shape))
+
+        arrs = [prep(src_xy, np.int32, (E, 2)), prep(src_int, np.float64, (E,)), prep(bkg, np.float64, (E,)),
+                prep(start_xy, np.int32, (E, A, 2)), prep(n_poly, np.int32, (E,)), prep(edges, np.float32, (E, 20, 4))]
+        ptrs = [None if a is None else a.ctypes.data_as(C.c_void_p) for a in arrs]
+        with self._torch.cuda.device(self.device):
+            _lib.check(self._L.rt_env_set_scenario(self._h, *ptrs), "rt_env_set_scenario")
+
+    def inject_uniforms(self, u) -> None:
+        """Test hook: Poisson sampler reads u[E, A, K] instead of Philox (None switches back)."""
+        if u is None:
+            self._inj = None
+            _lib.check(self._L.rt_env_inject_uniforms(self._h, None, 0))
+            return
+        t = self._torch.as_tensor(np.ascontiguousarray(u, dtype=np.float64)).reshape(self.E, self.A, -1)
+        self._inj = t.to(self.device).contiguous()
+        _lib.check(self._L.rt_env_inject_uniforms(self._h, self._inj.data_ptr(), self._inj.shape[2]))
+
+    def errors(self) -> int:
+        """OR of all envs' sticky RT_FLAG_* bits (synchronises)."""
+        f = C.c_int32(0)
+        _lib.check(self._L.rt_env_errors(self._h, C.byref(f), self._stream()))
+        return f.value
+
+    @property
+    def launches(self) -> int:
+        return int(self._L.rt_env_launch_count(self._h))
+
+    def _maps_ptr(self, out_maps):
+        m = self.obs_maps if out_maps is None else out_maps
+        if m is None:
+            return None, None
+        assert m.is_cuda and m.dtype == self._torch.float32 and m.is_contiguous()
+        assert m.numel() == self.E * 3 * self.G * self.G
+        return m, m.data_ptr()
+
+    def _info(self, xy) -> Dict[str, Any]:
+        # the reference's oracle view {agent, target, distance} (simple_gridworld.py:192-195)
+        return {"agent": xy, "target": self.buffer("SRC_XY"), "distance": self.buffer("PREV_DIST"),
+                "count": self.buffer("LAST_COUNT"), "maps": self.obs_maps}
+
+    # -- Gymnasium protocol --------------------------------------------------------------------
+    def reset(self, seed: Optional[int] = None, options: Optional[Dict] = None, mask=None, out_maps=None,
+              host: bool = False):
+        """SimpleGrid.reset (simple_gridworld.py:114-129), batched; ``mask`` selects envs."""
+        torch = self._torch
+        maps, mptr = self._maps_ptr(out_maps)
+        with torch.cuda.device(self.device):
+            if host or isinstance(mask, np.ndarray):
+                hxy, _, _ = self._host_bufs()
+                mk = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+                _lib.check(self._L.rt_env_reset_host(self._h, None if mk is None else mk.ctypes.data_as(C.c_void_p),
+                                                     hxy.data_ptr(), mptr, self._stream()), "rt_env_reset_host")
+                xy = hxy.numpy().copy()
+                return xy, {"agent": xy, "maps": maps}
+            mk = None
+            if mask is not None:
+                mk = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            _lib.check(self._L.rt_env_reset(self._h, None if mk is None else mk.data_ptr(), self.obs_xy.data_ptr(),
+                                            mptr, self._stream()), "rt_env_reset")
+        return self.obs_xy, self._info(self.obs_xy)
+
+    def step(self, actions, out_maps=None) -> Tuple[Any, Any, Any, Any, Dict[str, Any]]:
+        """SimpleGrid.step (simple_gridworld.py:131-167), batched, plus measurement and map rasterisation."""
+        torch = self._torch
+        maps, mptr = self._maps_ptr(out_maps)
+        with torch.cuda.device(self.device):
+            if isinstance(actions, torch.Tensor) and actions.is_cuda:
+                assert actions.dtype == torch.int32 and actions.is_contiguous() and actions.numel() == self.E * self.A
+                _lib.check(self._L.rt_env_step(self._h, actions.data_ptr(), self.obs_xy.data_ptr(), mptr,
+                                               self.reward.data_ptr(), self.done.data_ptr(), self._stream()),
+                           "rt_env_step")
+                return self.obs_xy, self.reward, self.done, False, self._info(self.obs_xy)
+            # host path
+            if isinstance(actions, torch.Tensor):
+                assert actions.dtype == torch.int32 and actions.is_contiguous()
+                aptr, keep = actions.data_ptr(), actions
+            else:
+                keep = np.ascontiguousarray(actions, dtype=np.int32)
+                aptr = keep.ctypes.data
+            assert (keep.numel() if hasattr(keep, "numel") else keep.size) == self.E * self.A
+            hxy, hrw, hdn = self._host_bufs()
+            rc = self._L.rt_env_step_host(self._h, aptr, hxy.data_ptr(), hrw.data_ptr(), hdn.data_ptr(), mptr,
+                                          self._stream())
+            if rc == _lib.RT_ERR_BAD_ACTION:
+                bad = np.asarray(keep).reshape(-1)
+                bad = bad[(bad < 1) | (bad > 4)]
+                raise ValueError(f"{int(bad[0])} is not a valid Action")  # IntEnum's message (:138)
+            _lib.check(rc, "rt_env_step_host")
+        xy = hxy.numpy()
+        return xy, hrw.numpy(), hdn.numpy(), False, {"agent": xy, "maps": maps}
+
+    def rasterize(self, out_maps=None):
+        maps, mptr = self._maps_ptr(out_maps)
+        with self._torch.cuda.device(self.device):
+            _lib.check(self._L.rt_env_rasterize(self._h, mptr, self._stream()), "rt_env_rasterize")
+        return maps
