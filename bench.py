@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py — agent-env-steps/s (observations rasterised) of the batched radiation-search env.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is ONE env step of every env of the workload: motion/collision/reward, measurement (line of
+sight + Poisson), per-env statistics and the rasterisation of the [E,3,32,32] observation tensor.  Every
+120 steps the rollout closes (batch Welford moments over the [120,E,A] readings, episode statistics,
+one all-gather + rank-ordered merge when N > 1) and all envs reset; that work is inside the timed region.
+
+Workloads (BASELINE.json configs):
+  c3 (default)  65,536 envs x 3 agents per GPU, 1-5 rectangular obstructions, G = 32, T = 120  — configs[2],
+                the 3-agent obstructed scenario the north-star target is quoted on; weak scaling
+                (N GPUs run N x 65,536 envs; Philox streams are keyed by the GLOBAL env id).
+  c2            4,096 envs x 1 agent, no obstructions (configs[1]) — a parity-size case, L2-resident.
+  c4            1,048,576 envs x 3 agents in total, split over the N ranks (configs[3]).
+
+One JSON line on stdout (rank 0).  `value`: inputs resident in HBM, CUDA-event time, max over ranks.
+`e2e`: the same loop through the host-buffer C-ABI entry points (rt_env_step_host): pinned actions copied
+up and obs_xy / reward / done copied back EVERY step inside the timed region, wall clock, max over ranks.
+`roofline`: the rasteriser (dominant kernel) timed live with CUDA events around its own launch.
+`cpu_baseline`: the CPU oracle (C port of the reference algorithm) on this box's host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+if str(REPO) not in sys.path:
+    sys.path.insert(0, str(REPO))
+
+T_EPISODE = 120
+GRID = 32
+METRIC = "agent-env-steps/sec (obs rasterised)"
+
+WORKLOADS = {
+    "c2": dict(envs=4096, agents=1, poly_min=0, poly_max=0, scaling="weak",
+               name="c2: 4,096 envs x 1 agent, 1 source, no obstructions, G=32, T=120 (BASELINE configs[1])"),
+    "c3": dict(envs=65536, agents=3, poly_min=1, poly_max=5, scaling="weak",
+               name="c3: 65,536 envs x 3 agents per GPU, 1-5 polygon obstructions (LOS attenuation), shared "
+                    "location/intensity/visit maps, G=32, T=120 (BASELINE configs[2]; N GPUs = N x 65,536 envs)"),
+    "c4": dict(envs=1048576, agents=3, poly_min=1, poly_max=5, scaling="strong",
+               name="c4: 1,048,576 envs x 3 agents sharded over the ranks, 1-5 polygon obstructions, G=32, T=120 "
+                    "(BASELINE configs[3])"),
+}
+
+
+def env_cfg(w, n_envs, base, seed=0):
+    return dict(n_envs=n_envs, n_agents=w["agents"], grid=GRID, max_steps=T_EPISODE, poly_min=w["poly_min"],
+                poly_max=w["poly_max"], rect_min=2, rect_max=6, lognorm_step=2, fixed_scenario=0, env_id_base=base,
+                seed=seed, cell_pitch_cm=100.0, min_dist_cm=50.0, transmission=0.0, src_lo=1e6, src_hi=1e7,
+                bkg_lo=10.0, bkg_hi=51.0)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU with NVML every 20 ms while running."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if bit and (r & bit):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def measured_peak_gbs():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def ncu_traffic_per_launch(n_envs):
+    """dram bytes per raster launch from the committed ncu capture, scaled per env (profiles/)."""
+    p = REPO / "profiles" / "raster_traffic.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return float(d["dram_bytes_per_env"]) * n_envs
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(w, n_envs, steps, warmup, threads, seconds=None):
+    """Time the CPU oracle (all `threads` host threads) on `n_envs` envs of the workload.
+    Returns (agent-steps/s, steps actually timed)."""
+    import numpy as np
+
+    from oracle import oracle as O
+
+    A = w["agents"]
+    env = O.OracleEnv(**env_cfg(w, n_envs, 0))
+    used = env.set_threads(threads)
+    rng = np.random.default_rng(0)
+    acts = rng.integers(1, 5, size=(T_EPISODE, n_envs, A)).astype(np.int32)
+    xy = np.zeros((n_envs, A, 2), np.int32)
+    rew = np.zeros((n_envs, A), np.int32)
+    done = np.zeros((n_envs, A), np.uint8)
+    maps = np.zeros((n_envs, 3, GRID, GRID), np.float32)
+    s = 0
+
+    def one():
+        nonlocal s
+        if s % T_EPISODE == 0:
+            env.reset(maps=False)
+        env.step_into(acts[s % T_EPISODE], xy, maps, rew, done)
+        s += 1
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    n = 0
+    if seconds is not None:
+        while time.perf_counter() - t0 < seconds:
+            one()
+            n += 1
+    else:
+        for _ in range(steps):
+            one()
+            n += 1
+    dt = time.perf_counter() - t0
+    return n_envs * A * n / dt, n, used
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference algorithm's CPU implementation on this box's host cores.
+    The reference is Python and cannot travel (no /root/reference on the GPU box), so this is the
+    oracle's C port of it (oracle/rt_oracle.c), OpenMP over envs with every host thread."""
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    n_envs = min(args.ref_envs, w["envs"])
+    rate, n, used = cpu_oracle_rate(w, n_envs, args.steps, max(args.warmup, 3), threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "agent-env-steps/s", "n_gpus": args.gpus,
+        "steps": n, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * n_envs * w["agents"] / rate,
+        "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["name"], "sample_envs": n_envs, "agents": w["agents"], "grid": GRID,
+                   "episode_steps": T_EPISODE},
+        "cpu_baseline": {"value": rate, "unit": "agent-env-steps/s", "cores": used, "kind": "port",
+                         "sample": f"{n_envs} envs x {w['agents']} agents x {n} steps of the workload's scenario, "
+                                   f"C oracle, {used} OpenMP threads"},
+        "e2e": {"value": rate, "unit": "agent-env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from rad_team_b200.distributed import merge_rollout_stats, shard_range
+    from rad_team_b200.envs import BatchedRadSearchEnv
+    from rad_team_b200.math_utils import RunningMoments
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = WORKLOADS[args.workload]
+    A = w["agents"]
+    if args.envs:
+        E, base = args.envs, rank * args.envs
+    elif w["scaling"] == "strong":
+        base, E = shard_range(w["envs"], rank, world)
+    else:
+        E, base = w["envs"], rank * w["envs"]
+    K, W = args.steps, max(args.warmup, 3)
+
+    env = BatchedRadSearchEnv(**env_cfg(w, E, base))
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    actions = torch.randint(1, 5, (T_EPISODE, E, A), dtype=torch.int32, device=dev, generator=gen)
+    rollout = torch.zeros((T_EPISODE, E, A), dtype=torch.float32, device=dev)
+    env.set_rollout(rollout)
+    moments = RunningMoments()
+    ep_stats = torch.zeros(3, dtype=torch.float64, device=dev)
+    extra_launches = [0]
+
+    def close_rollout():
+        moments.update(rollout.view(-1))      # k_moments_partial + k_moments_final
+        env.episode_stats(ep_stats)           # k_episode_stats (counted by the handle)
+        merge_rollout_stats(moments, ep_stats)  # all-gather (NCCL when world > 1) + k_moments_merge
+        extra_launches[0] += 3
+
+    state = {"s": 0}
+
+    def dev_step():
+        s = state["s"]
+        t = s % T_EPISODE
+        if t == 0:
+            if s > 0:
+                close_rollout()
+            env.reset()
+        env.step(actions[t])
+        state["s"] = s + 1
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local_rank)
+    # ---- device-resident throughput ("value") -------------------------------------------------
+    for _ in range(W):
+        dev_step()
+    barrier()
+    sampler.start()
+    l0 = env.launches
+    x0 = extra_launches[0]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(K):
+        dev_step()
+    ev1.record()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = (env.launches - l0) + (extra_launches[0] - x0)
+    flags = env.errors()
+
+    # ---- dominant kernel, live: the rasteriser alone, CUDA events around its own launch ----------
+    n_prof = min(K, 120)
+    pairs = []
+    step_pairs = []
+    env.reset()
+    for i in range(n_prof):
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        env.step(actions[i % T_EPISODE], rasterize=False)
+        b.record()
+        env.rasterize()
+        c.record()
+        step_pairs.append((a, b))
+        pairs.append((b, c))
+    torch.cuda.synchronize()
+    raster_ms = sum(p.elapsed_time(q) for p, q in pairs) / n_prof
+    kstep_ms = sum(p.elapsed_time(q) for p, q in step_pairs) / n_prof
+    state["s"] = 0
+
+    # ---- end to end through the host-buffer C ABI ("e2e") ----------------------------------------
+    h_actions = torch.randint(1, 5, (T_EPISODE, E, A), dtype=torch.int32).pin_memory()
+    hs = {"s": 0}
+
+    def host_step():
+        s = hs["s"]
+        t = s % T_EPISODE
+        if t == 0:
+            if s > 0:
+                close_rollout()
+            env.reset(host=True)
+        xy, rew, done, _, _ = env.step(h_actions[t])  # H2D actions, kernels, D2H obs/reward/done, sync
+        hs["s"] = s + 1
+        return rew
+
+    K2 = min(K, args.e2e_steps) if args.e2e_steps else K
+    for _ in range(W):
+        host_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K2):
+        host_step()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    clocks = sampler.stop()
+
+    total_agents = (w["envs"] if w["scaling"] == "strong" and not args.envs else E * world) * A
+    value = total_agents * K / (ms_total * 1e-3)
+    e2e_value = total_agents * K2 / e2e_s
+
+    peak, peak_src = measured_peak_gbs()
+    raster_bytes = E * (3 * GRID * GRID * 4 + GRID * GRID * (2 + 4))  # 18,432 B / env-step
+    achieved = raster_bytes / (raster_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic_per_launch(E), "kernel": "k_raster_vec", "ms_per_launch": raster_ms,
+                "algorithmic_bytes_per_launch": raster_bytes, "peak_source": peak_src,
+                "regime": "HBM (per-launch footprint %.0f MB >> 126 MB L2)" % (raster_bytes / 1e6)
+                if raster_bytes > 4 * 126e6 else "L2-resident footprint (%.0f MB)" % (raster_bytes / 1e6)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n_s = min(args.ref_envs, E)
+        rate, n, used = cpu_oracle_rate(w, n_s, 0, 3, threads, seconds=args.cpu_seconds)
+        cpu = {"value": rate, "unit": "agent-env-steps/s", "cores": used, "kind": "port",
+               "sample": f"{n_s} envs x {A} agents x {n} steps (~{args.cpu_seconds:.0f} s) of the same scenario, "
+                         f"C oracle of the reference algorithm, {used} OpenMP threads"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "agent-env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["name"], "envs_per_gpu": E, "agents": A, "grid": GRID, "episode_steps": T_EPISODE,
+                       "l2": "inputs larger than L2: each step streams %.0f MB per GPU" % (raster_bytes / 1e6),
+                       "rollout_close": "every 120 steps: batch Welford moments + episode stats"
+                                        + (" + NCCL all-gather/merge" if world > 1 else "") + " + reset, inside the timed region",
+                       "arithmetic": "fp64 physics/statistics, fp32 geometry and maps, int32 indices/counts"},
+            "roofline": roofline,
+            "kernels": {"k_raster_vec_ms": raster_ms, "k_step_ms": kstep_ms},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "agent-env-steps/s", "h2d_bytes_per_step": E * A * 4,
+                    "d2h_bytes_per_step": E * A * 13, "steps": K2,
+                    "note": "rt_env_step_host per step: pinned int32 actions up; obs_xy, reward, done down; maps are "
+                            "rasterised into the device-resident CNN input tensor"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "error_flags": flags,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1200)
+    ap.add_argument("--warmup", type=int, default=120)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
+    ap.add_argument("--ref-envs", type=int, default=4096, help="envs in the CPU sample")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (see the module docstring)")
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -123,7 +123,9 @@ typedef enum rt_buf {
   RT_BUF_LAST_Z = 23,    /* double [E][A]   standardised estimate            */
   RT_BUF_LAST_VALUE = 24,/* double [E][A]   normalised value written to the map */
   RT_BUF_VISIT_LUT = 25, /* float  [T*A+1]  BensLogNormalizer table          */
-  RT_BUF__COUNT = 26
+  RT_BUF_EP_RETURN = 26, /* int32  [E][A]   sum of rewards since reset       */
+  RT_BUF_EP_DONE = 27,   /* uint8  [E][A]   1 once the agent has reached the source this episode */
+  RT_BUF__COUNT = 28
 } rt_buf;
 
 int rt_abi_version(void);
@@ -180,6 +182,18 @@ int rt_env_rasterize(rt_env* env, float* obs_maps_dev, void* stream);
  * back to Philox.  The pointer must stay valid until replaced. */
 int rt_env_inject_uniforms(rt_env* env, const double* u_dev, int32_t k_per_agent);
 
+/* Rollout sink: when set, every step also stores each agent's Poisson count as
+ * fp32 into readings_dev [T][E][A] at row `tick` (the env's step index in its
+ * episode) — the buffer rt_moments_update() consumes at the end of a rollout.
+ * NULL detaches.  The pointer must stay valid until replaced. */
+int rt_env_set_rollout(rt_env* env, float* readings_dev);
+
+/* Episode statistics of the current episodes, reduced over all (env, agent):
+ * stats_dev double [3] = { sum of returns, sum of episode lengths (steps),
+ * number of agents that reached the source }.  What each rank contributes,
+ * next to its moments, to the once-per-rollout all-gather. */
+int rt_env_episode_stats(rt_env* env, double* stats_dev, void* stream);
+
 /* Raw device view of one state array (see rt_buf). */
 int rt_env_buffer(rt_env* env, int which, void** dev_ptr, size_t* bytes);
 /* OR of all envs' sticky flags -> *flags_host.  Synchronises `stream`. */
@@ -219,8 +233,10 @@ int rt_moments_standardize(rt_moments* m, const float* x_dev, float* out_dev, in
  * contributes to the all-gather). */
 int rt_moments_state(rt_moments* m, void** state_dev);
 /* Replace the state by the Chan merge, in rank order 0..n_ranks-1, of the
- * gathered triples double [n_ranks][3] (device). */
-int rt_moments_merge(rt_moments* m, const double* gathered_dev, int32_t n_ranks, void* stream);
+ * gathered triples: rank r's {count, mean, M2} starts at
+ * gathered_dev[r * stride_doubles] (device; stride >= 3). */
+int rt_moments_merge(rt_moments* m, const double* gathered_dev, int32_t n_ranks,
+                     int32_t stride_doubles, void* stream);
 
 /* ---- Normalizer / BensLogNormalizer: src/math_utils/normalize.py ---------- */
 

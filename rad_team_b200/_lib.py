@@ -20,6 +20,7 @@ BUF = dict(
     AGENT_XY=0, PREV_DIST=1, START_XY=2, SRC_XY=3, SRC_INT=4, BKG=5, N_POLY=6, EDGES=7, TICK=8, EPISODE=9,
     VISIT=10, INTENSITY=11, HEAD=12, LOG=13, WELFORD=15, WELFORD_N=16, EST_MAXMIN=17, FLAGS=18,
     LAST_COUNT=19, LAST_LOS=20, LAST_LAMBDA=21, LAST_EST=22, LAST_Z=23, LAST_VALUE=24, VISIT_LUT=25,
+    EP_RETURN=26, EP_DONE=27,
 )
 
 
@@ -50,6 +51,8 @@ SYMBOLS = {
     "rt_env_step_host": (C.c_int, [_vp] * 7),
     "rt_env_rasterize": (C.c_int, [_vp, _vp, _vp]),
     "rt_env_inject_uniforms": (C.c_int, [_vp, _vp, _i32]),
+    "rt_env_set_rollout": (C.c_int, [_vp, _vp]),
+    "rt_env_episode_stats": (C.c_int, [_vp, _vp, _vp]),
     "rt_env_buffer": (C.c_int, [_vp, C.c_int, _pp, C.POINTER(C.c_size_t)]),
     "rt_env_errors": (C.c_int, [_vp, C.POINTER(_i32), _vp]),
     "rt_env_launch_count": (_i64, [_vp]),
@@ -65,7 +68,7 @@ SYMBOLS = {
     "rt_moments_update": (C.c_int, [_vp, _vp, _i64, _vp]),
     "rt_moments_standardize": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "rt_moments_state": (C.c_int, [_vp, _pp]),
-    "rt_moments_merge": (C.c_int, [_vp, _vp, _i32, _vp]),
+    "rt_moments_merge": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
     "rt_normalize": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "rt_lognormalize": (C.c_int, [_vp, _dbl, _i32, _vp, _vp, _i64, _vp]),
     "rt_estimator_create": (C.c_int, [_i64, _i32, _i32, _pp]),

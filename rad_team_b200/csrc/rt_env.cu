@@ -56,6 +56,31 @@ bool is_pinned_or_device(const void* p) {
          at.type == cudaMemoryTypeDevice;
 }
 
+// {sum of returns, sum of episode lengths, agents that reached the source}: integer partial sums per
+// thread, warp-reduced, one fp64 atomicAdd per warp (integers well below 2^53: order-independent).
+__global__ void __launch_bounds__(256)
+k_episode_stats(const int32_t* __restrict__ ep_return, const uint8_t* __restrict__ ep_done,
+                const int32_t* __restrict__ tick, int E, int A, double* __restrict__ out) {
+  long long ret = 0, len = 0, dn = 0;
+  const long long n = (long long)E * A;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    ret += ep_return[i];
+    dn += ep_done[i];
+    len += tick[i / A];
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    ret += __shfl_down_sync(0xffffffffu, ret, off);
+    len += __shfl_down_sync(0xffffffffu, len, off);
+    dn += __shfl_down_sync(0xffffffffu, dn, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out + 0, (double)ret);
+    atomicAdd(out + 1, (double)len);
+    atomicAdd(out + 2, (double)dn);
+  }
+}
+
 __global__ void k_or_flags(const int32_t* __restrict__ flags, int n, int32_t* __restrict__ out) {
   int v = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v |= flags[i];
@@ -159,7 +184,8 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
       /*HEAD*/ E * cells * 2,   /*LOG*/ (size_t)cap * E * 8, /*unused*/ 0,       /*WELFORD*/ E * 48,
       /*WELFORD_N*/ E * 4,      /*EST_MAXMIN*/ E * 16,   /*FLAGS*/ E * 4,        /*LAST_COUNT*/ E * A * 4,
       /*LAST_LOS*/ E * A,       /*LAST_LAMBDA*/ E * A * 8, /*LAST_EST*/ E * A * 8, /*LAST_Z*/ E * A * 8,
-      /*LAST_VALUE*/ E * A * 8, /*VISIT_LUT*/ ((size_t)cap + 1) * 4};
+      /*LAST_VALUE*/ E * A * 8, /*VISIT_LUT*/ ((size_t)cap + 1) * 4, /*EP_RETURN*/ E * A * 4,
+      /*EP_DONE*/ E * A};
   Carver cv;
   size_t off[RT_BUF__COUNT];
   for (int i = 0; i < RT_BUF__COUNT; ++i) off[i] = cv.take(sz[i]);
@@ -225,6 +251,9 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
   d.last_z = (double*)h->buf_ptr[RT_BUF_LAST_Z];
   d.last_value = (double*)h->buf_ptr[RT_BUF_LAST_VALUE];
   d.lut = (float*)h->buf_ptr[RT_BUF_VISIT_LUT];
+  d.ep_return = (int32_t*)h->buf_ptr[RT_BUF_EP_RETURN];
+  d.ep_done = (uint8_t*)h->buf_ptr[RT_BUF_EP_DONE];
+  d.rollout = nullptr;
   d.inj = nullptr;
   d.inj_k = 0;
 
@@ -378,6 +407,25 @@ int rt_env_inject_uniforms(rt_env* h, const double* u_dev, int32_t k_per_agent) 
   if (!h || (u_dev && k_per_agent < 1)) return RT_ERR_BAD_ARG;
   h->dev.inj = u_dev;
   h->dev.inj_k = u_dev ? k_per_agent : 0;
+  return RT_OK;
+}
+
+int rt_env_set_rollout(rt_env* h, float* readings_dev) {
+  if (!h) return RT_ERR_BAD_ARG;
+  h->dev.rollout = readings_dev;
+  return RT_OK;
+}
+
+int rt_env_episode_stats(rt_env* h, double* stats_dev, void* stream) {
+  if (!h || !stats_dev) return RT_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  RT_CUDA(cudaMemsetAsync(stats_dev, 0, 3 * sizeof(double), st));
+  long long blocks = ((long long)h->dev.E * h->dev.A + 255) / 256;
+  if (blocks > h->n_sm * 8) blocks = h->n_sm * 8;
+  k_episode_stats<<<(unsigned)blocks, 256, 0, st>>>(h->dev.ep_return, h->dev.ep_done, h->dev.tick, h->dev.E,
+                                                  h->dev.A, stats_dev);
+  h->launches += 1;
+  RT_CUDA_LAUNCH_CHECK();
   return RT_OK;
 }
 

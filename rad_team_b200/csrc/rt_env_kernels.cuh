@@ -48,6 +48,9 @@ struct EnvDev {
   double* last_z;
   double* last_value;
   float* lut;  // [cap+1]
+  int32_t* ep_return;  // [E][A]
+  uint8_t* ep_done;    // [E][A]
+  float* rollout;      // [T][E][A] readings sink, or nullptr
   const double* inj;
   int inj_k;
 };
@@ -221,6 +224,8 @@ k_step(const EnvDev d, const int32_t* __restrict__ actions, int32_t* __restrict_
       reinterpret_cast<int2*>(obs_xy)[ia] = make_int2(nx, ny);
       reward[ia] = rw;
       done[ia] = dn ? 1 : 0;
+      d.ep_return[ia] += rw;
+      if (dn) d.ep_done[ia] = 1;
 
       // N2 + N1: obstructions on the line of sight, expected count
       const int nb = np > 0 ? polys_crossed(my_edges, np, (float)nx + 0.5f, (float)ny + 0.5f,
@@ -247,6 +252,7 @@ k_step(const EnvDev d, const int32_t* __restrict__ actions, int32_t* __restrict_
       s.cell[t] = ny * d.G + nx;
       s.count[t] = (int)cnt;
       d.last_count[ia] = (int)cnt;
+      if (d.rollout != nullptr) d.rollout[((size_t)tick * d.E + e) * A + a] = (float)cnt;
       d.last_los[ia] = (uint8_t)nb;
       d.last_lambda[ia] = lam;
     }
@@ -411,6 +417,8 @@ k_reset_state(const EnvDev d, const uint8_t* __restrict__ mask, int32_t* __restr
     d.prev_dist[ia] = abs(p.x - src.x) + abs(p.y - src.y);  // :121
     if (obs_xy) reinterpret_cast<int2*>(obs_xy)[ia] = p;
     d.last_count[ia] = 0;
+    d.ep_return[ia] = 0;
+    d.ep_done[ia] = 0;
     d.last_los[ia] = 0;
     d.last_lambda[ia] = 0.0;
     d.last_est[ia] = 0.0;

@@ -274,11 +274,12 @@ __global__ void k_moments_final(const double* __restrict__ partials, int n_parti
 }
 
 // rank-ordered merge of gathered triples (strictly sequential: bit-identical on every rank)
-__global__ void k_moments_merge(const double* __restrict__ gathered, int n_ranks, double* __restrict__ state) {
+__global__ void k_moments_merge(const double* __restrict__ gathered, int n_ranks, int stride,
+                                double* __restrict__ state) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   Mom s = {0.0, 0.0, 0.0};
   for (int r = 0; r < n_ranks; ++r) {
-    Mom p = {gathered[3 * r], gathered[3 * r + 1], gathered[3 * r + 2]};
+    Mom p = {gathered[stride * r], gathered[stride * r + 1], gathered[stride * r + 2]};
     s = chan(s, p);
   }
   state[0] = s.n;
@@ -387,9 +388,10 @@ int rt_moments_state(rt_moments* m, void** state_dev) {
   return RT_OK;
 }
 
-int rt_moments_merge(rt_moments* m, const double* gathered_dev, int32_t n_ranks, void* stream) {
-  if (!m || !gathered_dev || n_ranks < 1) return RT_ERR_BAD_ARG;
-  k_moments_merge<<<1, 32, 0, (cudaStream_t)stream>>>(gathered_dev, n_ranks, m->state);
+int rt_moments_merge(rt_moments* m, const double* gathered_dev, int32_t n_ranks, int32_t stride_doubles,
+                     void* stream) {
+  if (!m || !gathered_dev || n_ranks < 1 || stride_doubles < 3) return RT_ERR_BAD_ARG;
+  k_moments_merge<<<1, 32, 0, (cudaStream_t)stream>>>(gathered_dev, n_ranks, stride_doubles, m->state);
   RT_CUDA_LAUNCH_CHECK();
   return RT_OK;
 }

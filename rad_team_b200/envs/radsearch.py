@@ -76,6 +76,8 @@ _BUF_SPEC = {
     "LAST_Z": ("float64", lambda E, A, c, cap: (E, A)),
     "LAST_VALUE": ("float64", lambda E, A, c, cap: (E, A)),
     "VISIT_LUT": ("float32", lambda E, A, c, cap: (cap + 1,)),
+    "EP_RETURN": ("int32", lambda E, A, c, cap: (E, A)),
+    "EP_DONE": ("uint8", lambda E, A, c, cap: (E, A)),
 }
 _ITEMSIZE = {"int32": 4, "float64": 8, "float32": 4, "uint16": 2, "uint8": 1}
 
@@ -182,6 +184,26 @@ class BatchedRadSearchEnv:
         self._inj = t.to(self.device).contiguous()
         _lib.check(self._L.rt_env_inject_uniforms(self._h, self._inj.data_ptr(), self._inj.shape[2]))
 
+    def set_rollout(self, readings) -> None:
+        """Attach a float32 CUDA tensor [T, E, A]: each step stores the agents' counts at row `tick`."""
+        if readings is None:
+            self._rollout = None
+            _lib.check(self._L.rt_env_set_rollout(self._h, None))
+            return
+        t = self._torch
+        assert readings.is_cuda and readings.dtype == t.float32 and readings.is_contiguous()
+        assert tuple(readings.shape) == (self.cfg.max_steps, self.E, self.A)
+        self._rollout = readings
+        _lib.check(self._L.rt_env_set_rollout(self._h, readings.data_ptr()))
+
+    def episode_stats(self, out=None):
+        """float64 CUDA tensor [3]: sum of returns, sum of episode lengths, agents that reached the source."""
+        t = self._torch
+        out = t.empty(3, dtype=t.float64, device=self.device) if out is None else out
+        with t.cuda.device(self.device):
+            _lib.check(self._L.rt_env_episode_stats(self._h, out.data_ptr(), self._stream()))
+        return out
+
     def errors(self) -> int:
         """OR of all envs' sticky RT_FLAG_* bits (synchronises)."""
         f = C.c_int32(0)
@@ -226,10 +248,11 @@ class BatchedRadSearchEnv:
                                             mptr, self._stream()), "rt_env_reset")
         return self.obs_xy, self._info(self.obs_xy)
 
-    def step(self, actions, out_maps=None) -> Tuple[Any, Any, Any, Any, Dict[str, Any]]:
-        """SimpleGrid.step (simple_gridworld.py:131-167), batched, plus measurement and map rasterisation."""
+    def step(self, actions, out_maps=None, rasterize: bool = True) -> Tuple[Any, Any, Any, Any, Dict[str, Any]]:
+        """SimpleGrid.step (simple_gridworld.py:131-167), batched, plus measurement and map rasterisation
+        (``rasterize=False`` leaves the maps to a later ``rasterize()`` call)."""
         torch = self._torch
-        maps, mptr = self._maps_ptr(out_maps)
+        maps, mptr = self._maps_ptr(out_maps) if rasterize else (None, None)
         with torch.cuda.device(self.device):
             if isinstance(actions, torch.Tensor) and actions.is_cuda:
                 assert actions.dtype == torch.int32 and actions.is_contiguous() and actions.numel() == self.E * self.A

@@ -158,10 +158,12 @@ class RunningMoments:
         return out
 
     def merge_gathered(self, gathered) -> None:
-        """state <- Chan merge, in rank order, of gathered float64 [n_ranks, 3] (device)."""
+        """state <- Chan merge, in rank order, of gathered float64 [n_ranks, >=3] (device): row r starts
+        with rank r's (count, mean, M2)."""
         t = self._torch
-        assert gathered.is_cuda and gathered.dtype == t.float64 and gathered.is_contiguous()
-        _lib.check(self._L.rt_moments_merge(self._h, gathered.data_ptr(), gathered.shape[0], self._stream()))
+        assert gathered.is_cuda and gathered.dtype == t.float64 and gathered.is_contiguous() and gathered.dim() == 2
+        _lib.check(self._L.rt_moments_merge(self._h, gathered.data_ptr(), gathered.shape[0], gathered.shape[1],
+                                            self._stream()))
 
     @property
     def count(self) -> float:

