@@ -112,7 +112,7 @@ def test_low_rate_multiplication_branch():
 def test_injected_uniforms_bit_exact_counts():
     import torch
 
-    g, o = make_pair(n_envs=300, n_agents=3, grid=32, max_steps=20, poly_min=1, poly_max=5, seed=8)
+    g, o = make_pair(n_envs=300, n_agents=3, grid=32, max_steps=30, poly_min=1, poly_max=5, seed=8)
     rng = np.random.default_rng(8)
     g.reset(); o.reset()
     for t in range(20):
