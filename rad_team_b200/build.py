@@ -48,7 +48,8 @@ def stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not stale():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", str(INCLUDE), "-o", str(LIB), *[str(CSRC / s) for s in SOURCES]]
+    extra = os.environ.get("RT_B200_NVCC_EXTRA", "").split()  # e.g. -DRT_STEP_MIN_CTAS=3 for A/B builds
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-I", str(INCLUDE), "-o", str(LIB), *[str(CSRC / s) for s in SOURCES]]
     # the image exports CC/CXX wrappers; let nvcc pick the distro host compiler
     env = dict(os.environ)
     if Path("/usr/bin/g++").exists():

@@ -1,5 +1,6 @@
 // rt_env.cu — host side of the batched environment: handle, device slab, launches, C ABI.
 // See include/rt_b200.h for the contract of every entry point.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -33,6 +34,11 @@ struct rt_env {
   int64_t launches = 0;
   int epb = 64;
   bool lut_in_smem = true;
+  bool overlap = false;  // RT_B200_OVERLAP=1: base image on the aux stream || k_step, then k_patch (measured slower)
+  cudaStream_t aux = nullptr;  // carries the base image concurrently with k_step
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int raster_ctas = 32, raster_unroll = 2;  // full rasteriser: CTAs per SM (grid cap), chunks in flight per thread
+  int base_ctas = 2, base_unroll = 4;       // base image: few resident CTAs so that k_step co-resides
 };
 
 namespace {
@@ -88,25 +94,43 @@ __global__ void k_or_flags(const int32_t* __restrict__ flags, int n, int32_t* __
   if ((threadIdx.x & 31) == 0 && v) atomicOr(out, v);
 }
 
+template <bool kAgents>
+void launch_raster_vec(rt_env* h, float* obs_maps, cudaStream_t st, int ctas_per_sm, int unroll) {
+  const EnvDev& d = h->dev;
+  const long long n_chunks = (long long)d.E * (d.cells >> 3);
+  const int threads = 256;
+  long long blocks = (n_chunks + threads - 1) / threads;
+  const long long cap_blocks = (long long)h->n_sm * ctas_per_sm;
+  if (blocks > cap_blocks) blocks = cap_blocks;
+  const size_t sm = h->lut_in_smem ? (size_t)(d.cap + 1) * 4 : 0;
+#define RT_LAUNCH_RV(U)                                                                                  \
+  do {                                                                                                   \
+    if (h->lut_in_smem)                                                                                  \
+      k_raster_vec<true, kAgents, U><<<(unsigned)blocks, threads, sm, st>>>(d, obs_maps, n_chunks);     \
+    else                                                                                                 \
+      k_raster_vec<false, kAgents, U><<<(unsigned)blocks, threads, 0, st>>>(d, obs_maps, n_chunks);     \
+  } while (0)
+  if (unroll >= 4)
+    RT_LAUNCH_RV(4);
+  else if (unroll >= 2)
+    RT_LAUNCH_RV(2);
+  else
+    RT_LAUNCH_RV(1);
+#undef RT_LAUNCH_RV
+  h->launches += 1;
+}
+
 int launch_raster(rt_env* h, float* obs_maps, cudaStream_t st) {
   const EnvDev& d = h->dev;
   if ((d.cells & 7) == 0) {
-    const long long n_chunks = (long long)d.E * (d.cells >> 3);
-    const int threads = 256;
-    long long blocks = (n_chunks + threads - 1) / threads;
-    const long long cap_blocks = (long long)h->n_sm * 8 * 4;  // a few waves of 8 resident CTAs / SM
-    if (blocks > cap_blocks) blocks = cap_blocks;
-    if (h->lut_in_smem)
-      k_raster_vec<true><<<(unsigned)blocks, threads, (size_t)(d.cap + 1) * 4, st>>>(d, obs_maps, n_chunks);
-    else
-      k_raster_vec<false><<<(unsigned)blocks, threads, 0, st>>>(d, obs_maps, n_chunks);
+    launch_raster_vec<true>(h, obs_maps, st, h->raster_ctas, h->raster_unroll);
   } else {
     const long long n = (long long)d.E * d.cells;
     long long blocks = (n + 255) / 256;
     if (blocks > (long long)h->n_sm * 32) blocks = (long long)h->n_sm * 32;
     k_raster_any<<<(unsigned)blocks, 256, 0, st>>>(d, obs_maps, n);
+    h->launches += 1;
   }
-  h->launches += 1;
   RT_CUDA_LAUNCH_CHECK();
   return RT_OK;
 }
@@ -116,6 +140,22 @@ int launch_step(rt_env* h, const int32_t* actions, int32_t* obs_xy, float* obs_m
   const EnvDev& d = h->dev;
   const int epb = h->epb;
   const unsigned blocks = (unsigned)((d.E + epb - 1) / epb);
+  if (obs_maps && (d.cells & 7) == 0 && h->overlap) {
+    // Overlapped step: the base image (location = 0, intensity / visit maps as they stand) streams on
+    // the auxiliary stream WHILE k_step runs on the caller's stream; the two only race on the <= A
+    // cells per env that this step changes, and k_patch rewrites exactly those from the final state.
+    RT_CUDA(cudaEventRecord(h->ev_fork, st));
+    RT_CUDA(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
+    launch_raster_vec<false>(h, obs_maps, h->aux, h->base_ctas, h->base_unroll);
+    RT_CUDA(cudaEventRecord(h->ev_join, h->aux));
+    k_step<<<blocks, epb * d.A, step_smem_bytes(epb, d.A), st>>>(d, actions, obs_xy, reward, done);
+    RT_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+    const long long n = (long long)d.E * d.A;
+    k_patch<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, obs_maps);
+    h->launches += 2;
+    RT_CUDA_LAUNCH_CHECK();
+    return RT_OK;
+  }
   k_step<<<blocks, epb * d.A, step_smem_bytes(epb, d.A), st>>>(d, actions, obs_xy, reward, done);
   h->launches += 1;
   RT_CUDA_LAUNCH_CHECK();
@@ -282,18 +322,36 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
                { rt_env_destroy(h); });
   }
   h->lut_in_smem = ((size_t)cap + 1) * 4 <= 32 * 1024;
-  // envs per CTA of k_step: <= 256 threads, and enough CTAs to cover the SMs twice when E allows
-  int epb = 256 / cfg->n_agents;
+  // envs per CTA of k_step: <= 192 threads, and enough CTAs to cover the SMs twice when E allows
+  int epb = 192 / cfg->n_agents;
   if (epb > 64) epb = 64;
   while (epb > 8 && (cfg->n_envs + epb - 1) / epb < 2 * h->n_sm) epb >>= 1;
   if (epb * cfg->n_agents < 32) epb = (32 + cfg->n_agents - 1) / cfg->n_agents;
   h->epb = epb;
+  if (const char* ev = std::getenv("RT_B200_EPB")) {  // tuning knob: envs per CTA of the step kernels
+    const int v = std::atoi(ev);
+    if (v >= 1 && v * cfg->n_agents <= 192) h->epb = v;
+  }
+  if (const char* ev = std::getenv("RT_B200_OVERLAP")) h->overlap = std::atoi(ev) != 0;
+  if (const char* ev = std::getenv("RT_B200_RASTER_CTAS")) h->raster_ctas = std::max(1, std::atoi(ev));
+  if (const char* ev = std::getenv("RT_B200_RASTER_UNROLL")) h->raster_unroll = std::max(1, std::atoi(ev));
+  if (const char* ev = std::getenv("RT_B200_BASE_CTAS")) h->base_ctas = std::max(1, std::atoi(ev));
+  if (const char* ev = std::getenv("RT_B200_BASE_UNROLL")) h->base_unroll = std::max(1, std::atoi(ev));
+  RT_CUDA_OR(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking), { rt_env_destroy(h); });
+  RT_CUDA_OR(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming), { rt_env_destroy(h); });
+  RT_CUDA_OR(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming), { rt_env_destroy(h); });
   *out = h;
   return RT_OK;
 }
 
 int rt_env_destroy(rt_env* h) {
   if (!h) return RT_OK;
+  if (h->aux) {
+    cudaStreamSynchronize(h->aux);
+    cudaStreamDestroy(h->aux);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->slab) cudaFree(h->slab);
   if (h->pinned) cudaFreeHost(h->pinned);
   delete h;
@@ -384,13 +442,21 @@ int rt_env_step_host(rt_env* h, const int32_t* actions_host, int32_t* obs_xy_hos
     a_src = p_act;
   }
   RT_CUDA(cudaMemcpyAsync(h->d_actions, a_src, n * 4, cudaMemcpyHostToDevice, st));
-  const int rc = launch_step(h, h->d_actions, h->d_obs_xy, obs_maps_dev, h->d_reward, h->d_done, st);
+  // k_step, then the small results travel back on the auxiliary stream WHILE the rasteriser streams
+  int rc = launch_step(h, h->d_actions, h->d_obs_xy, nullptr, h->d_reward, h->d_done, st);
   if (rc != RT_OK) return rc;
+  RT_CUDA(cudaEventRecord(h->ev_fork, st));
+  RT_CUDA(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
   const bool dx = is_pinned_or_device(obs_xy_host), dr = is_pinned_or_device(reward_host),
              dd = is_pinned_or_device(done_host);
-  RT_CUDA(cudaMemcpyAsync(dx ? (void*)obs_xy_host : (void*)p_xy, h->d_obs_xy, n * 8, cudaMemcpyDeviceToHost, st));
-  RT_CUDA(cudaMemcpyAsync(dr ? (void*)reward_host : (void*)p_rw, h->d_reward, n * 4, cudaMemcpyDeviceToHost, st));
-  RT_CUDA(cudaMemcpyAsync(dd ? (void*)done_host : (void*)p_dn, h->d_done, n, cudaMemcpyDeviceToHost, st));
+  RT_CUDA(cudaMemcpyAsync(dx ? (void*)obs_xy_host : (void*)p_xy, h->d_obs_xy, n * 8, cudaMemcpyDeviceToHost, h->aux));
+  RT_CUDA(cudaMemcpyAsync(dr ? (void*)reward_host : (void*)p_rw, h->d_reward, n * 4, cudaMemcpyDeviceToHost, h->aux));
+  RT_CUDA(cudaMemcpyAsync(dd ? (void*)done_host : (void*)p_dn, h->d_done, n, cudaMemcpyDeviceToHost, h->aux));
+  if (obs_maps_dev) {
+    rc = launch_raster(h, obs_maps_dev, st);
+    if (rc != RT_OK) return rc;
+  }
+  RT_CUDA(cudaStreamSynchronize(h->aux));
   RT_CUDA(cudaStreamSynchronize(st));
   if (!dx) std::memcpy(obs_xy_host, p_xy, n * 8);
   if (!dr) std::memcpy(reward_host, p_rw, n * 4);

@@ -108,26 +108,117 @@ struct StepSmem {  // carved from dynamic shared memory, see step_smem_bytes()
   int* eflags;     // [epb]  flags raised by the agents' samplers
   int* cell;       // [epb*A]
   int* count;      // [epb*A]
+  int* pre_vh;     // [epb*A]  prefetched visit count | head << 16 of the agent's new cell
+  uint2* pre_node; // [epb*A]  prefetched first (smallest) log entry of that cell
   uint64_t* bar;
 };
 __host__ __device__ inline size_t step_smem_bytes(int epb, int A) {
-  return 16 + (size_t)epb * kEdgeRowF4 * 16 + (size_t)epb * 3 * 4 + (size_t)epb * A * 2 * 4;
+  return 16 + (size_t)epb * kEdgeRowF4 * 16 + (size_t)epb * A * 8 + (size_t)epb * 3 * 4 +
+         (size_t)epb * A * 3 * 4;
 }
 
-__global__ void __launch_bounds__(256)
-k_step(const EnvDev d, const int32_t* __restrict__ actions, int32_t* __restrict__ obs_xy,
-       int32_t* __restrict__ reward, uint8_t* __restrict__ done) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+// K4a: the env's agents feed ONE estimator / Welford / normaliser, in agent order (one thread per env).
+__device__ __forceinline__ void stats_chain(const EnvDev& d, const StepSmem& s, int e, int le, int tick,
+                                            WelfordState& w, double emx, double emn) {
+  const int A = d.A;
+  uint16_t* visit = d.visit + (size_t)e * d.cells;
+  uint16_t* head = d.head + (size_t)e * d.cells;
+  float* inten = d.inten + (size_t)e * d.cells;
+  uint2* log = d.log + e;  // entry i at log[i * E]
+  const size_t E = (size_t)d.E;
+  int fl = s.eflags[le];
+  for (int aa = 0; aa < A; ++aa) {
+    const int cell = s.cell[le * A + aa];
+    const int cnt = s.count[le * A + aa];
+    const int idx = tick * A + aa;
+    bool clash = false;  // an earlier agent of this env wrote this cell in this very step
+    for (int bb = 0; bb < aa; ++bb) clash |= s.cell[le * A + bb] == cell;
+    int n, cur;  // readings at this cell including this one; list cursor (entry + 1, 0 = end)
+    uint2 nd = make_uint2(0u, 0u);
+    bool have = false;
+    if (!clash) {
+      const unsigned vh = (unsigned)s.pre_vh[le * A + aa];
+      n = (int)(vh & 0xffffu) + 1;
+      cur = (int)(vh >> 16);
+      nd = s.pre_node[le * A + aa];
+      have = cur != 0;
+    } else {
+      n = (int)visit[cell] + 1;
+      cur = (int)head[cell];
+    }
+    visit[cell] = (uint16_t)n;
+
+    // a9: IntensityResamplingEstimator.update + get_estimate (estimator.py:31-48,61-70).
+    // The cell's readings form a linked list sorted by value; insert the new reading and
+    // pick the median (elements (n-1)/2 and n/2 of the new list) in the same walk.
+    const int k1 = (n - 1) >> 1, k2 = n >> 1;
+    int pred = 0;
+    bool inserted = false;
+    int m1 = 0, m2 = 0;
+    for (int i = 0; i <= k2 || !inserted; ++i) {
+      if (cur != 0 && !have) {
+        nd = log[(size_t)(cur - 1) * E];
+        have = true;
+      }
+      int elem;
+      if (!inserted && (cur == 0 || (int)nd.x > cnt)) {
+        elem = cnt;
+        inserted = true;
+        log[(size_t)idx * E] = make_uint2((uint32_t)cnt, (uint32_t)cur);
+        if (pred == 0)
+          head[cell] = (uint16_t)(idx + 1);
+        else
+          log[(size_t)(pred - 1) * E].y = (uint32_t)(idx + 1);
+      } else {
+        elem = (int)nd.x;
+        pred = cur;
+        cur = (int)nd.y;
+        have = false;
+      }
+      if (i == k1) m1 = elem;
+      if (i == k2) m2 = elem;
+    }
+    const double est = (n & 1) ? (double)m2 : __ddiv_rn((double)((long long)m1 + (long long)m2), 2.0);
+    est_maxmin(est, emx, emn);
+
+    // a6: Welford update + z-score; a7: min-max against the running z range
+    const double z = welford_update(w, est);
+    double val;
+    if (!normalize_minmax(z, w.zmax, true, w.zmin, val)) {
+      fl |= RT_FLAG_NORMALIZE;
+      val = 0.0;
+    }
+    inten[cell] = (float)val;
+    const size_t ia = (size_t)e * A + aa;
+    d.last_est[ia] = est;
+    d.last_z[ia] = z;
+    d.last_value[ia] = val;
+  }
+  double2* wp = reinterpret_cast<double2*>(d.welford + (size_t)e * 6);
+  wp[0] = make_double2(w.mean, w.m2);
+  wp[1] = make_double2(w.var, w.sd);
+  wp[2] = make_double2(w.zmax, w.zmin);
+  d.welford_n[e] = w.count;
+  reinterpret_cast<double2*>(d.est_mm)[e] = make_double2(emx, emn);
+  d.tick[e] = tick + 1;
+  if (fl) atomicOr(&d.flags[e], fl);
+}
+
+__device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __restrict__ actions,
+                                          int32_t* __restrict__ obs_xy, int32_t* __restrict__ reward,
+                                          uint8_t* __restrict__ done, unsigned char* smem_raw) {
   const int A = d.A;
   const int epb = blockDim.x / A;
   StepSmem s;
   s.bar = reinterpret_cast<uint64_t*>(smem_raw);
   s.edges = reinterpret_cast<float4*>(smem_raw + 16);
-  s.n_poly = reinterpret_cast<int*>(smem_raw + 16 + (size_t)epb * kEdgeRowF4 * 16);
+  s.pre_node = reinterpret_cast<uint2*>(smem_raw + 16 + (size_t)epb * kEdgeRowF4 * 16);
+  s.n_poly = reinterpret_cast<int*>(s.pre_node + epb * A);
   s.skip = s.n_poly + epb;
   s.eflags = s.skip + epb;
   s.cell = s.eflags + epb;
   s.count = s.cell + epb * A;
+  s.pre_vh = s.count + epb * A;
 
   const int t = threadIdx.x;
   const int le = t / A;
@@ -200,6 +291,7 @@ k_step(const EnvDev d, const int32_t* __restrict__ actions, int32_t* __restrict_
       reinterpret_cast<int2*>(obs_xy)[ia] = pos;
       reward[ia] = 0;
       done[ia] = 0;
+      s.cell[t] = pos.y * d.G + pos.x;
     } else {
       const float4* my_edges = s.edges + (size_t)le * kEdgeRowF4;
       np = s.n_poly[le];
@@ -227,6 +319,13 @@ k_step(const EnvDev d, const int32_t* __restrict__ actions, int32_t* __restrict_
       d.ep_return[ia] += rw;
       if (dn) d.ep_done[ia] = 1;
 
+      // Prefetch what the per-env statistics chain will need for this cell (visit count, list head,
+      // first list entry): the loads fly while the line-of-sight tests and the sampler compute.
+      const int cell = ny * d.G + nx;
+      const size_t mcell = (size_t)e * d.cells + cell;
+      const unsigned pv = d.visit[mcell];
+      const unsigned ph = d.head[mcell];
+
       // N2 + N1: obstructions on the line of sight, expected count
       const int nb = np > 0 ? polys_crossed(my_edges, np, (float)nx + 0.5f, (float)ny + 0.5f,
                                             (float)src.x + 0.5f, (float)src.y + 0.5f)
@@ -237,6 +336,9 @@ k_step(const EnvDev d, const int32_t* __restrict__ actions, int32_t* __restrict_
       double strength = src_int;
       for (int i = 0; i < nb; ++i) strength = __dmul_rn(strength, d.transmission);
       const double lam = __dadd_rn(__ddiv_rn(strength, d2), bkg);
+
+      uint2 pnode = make_uint2(0u, 0u);
+      if (ph != 0u) pnode = d.log[(size_t)(ph - 1) * d.E + e];
 
       // N3: Poisson count
       Draws dr;
@@ -249,8 +351,10 @@ k_step(const EnvDev d, const int32_t* __restrict__ actions, int32_t* __restrict_
       const long long cnt = poisson_draw(lam, dr, fl);
       if (fl) atomicOr(&s.eflags[le], fl);
 
-      s.cell[t] = ny * d.G + nx;
+      s.cell[t] = cell;
       s.count[t] = (int)cnt;
+      s.pre_vh[t] = (int)(pv | (ph << 16));
+      s.pre_node[t] = pnode;
       d.last_count[ia] = (int)cnt;
       if (d.rollout != nullptr) d.rollout[((size_t)tick * d.E + e) * A + a] = (float)cnt;
       d.last_los[ia] = (uint8_t)nb;
@@ -259,82 +363,22 @@ k_step(const EnvDev d, const int32_t* __restrict__ actions, int32_t* __restrict_
   }
   __syncthreads();  // readings of all agents are in shared memory
 
-  if (!valid || a != 0) return;
-  if (skip) {
-    atomicOr(&d.flags[e], skip);
-    return;
+  if (valid && a == 0) {
+    if (skip)
+      atomicOr(&d.flags[e], skip);
+    else
+      stats_chain(d, s, e, le, tick, w, emx, emn);
   }
-  // K4a: the env's agents feed ONE estimator / Welford / normaliser, in agent order.
-  uint16_t* visit = d.visit + (size_t)e * d.cells;
-  uint16_t* head = d.head + (size_t)e * d.cells;
-  float* inten = d.inten + (size_t)e * d.cells;
-  uint2* log = d.log + e;  // entry i at log[i * E]
-  const size_t E = (size_t)d.E;
-  int fl = s.eflags[le];
-  for (int aa = 0; aa < A; ++aa) {
-    const int cell = s.cell[le * A + aa];
-    const int cnt = s.count[le * A + aa];
-    const int idx = tick * A + aa;
-    const int n = (int)visit[cell] + 1;  // readings at this cell including this one
-    visit[cell] = (uint16_t)n;
+}
 
-    // a9: IntensityResamplingEstimator.update + get_estimate (estimator.py:31-48,61-70).
-    // The cell's readings form a linked list sorted by value; insert the new reading and
-    // pick the median (elements (n-1)/2 and n/2 of the new list) in the same walk.
-    const int k1 = (n - 1) >> 1, k2 = n >> 1;
-    int cur = (int)head[cell];  // encoded idx+1, 0 = end
-    int pred = 0;
-    bool inserted = false;
-    int m1 = 0, m2 = 0;
-    uint2 nd = make_uint2(0u, 0u);
-    bool have = false;
-    for (int i = 0; i <= k2 || !inserted; ++i) {
-      if (cur != 0 && !have) {
-        nd = log[(size_t)(cur - 1) * E];
-        have = true;
-      }
-      int elem;
-      if (!inserted && (cur == 0 || (int)nd.x > cnt)) {
-        elem = cnt;
-        inserted = true;
-        log[(size_t)idx * E] = make_uint2((uint32_t)cnt, (uint32_t)cur);
-        if (pred == 0)
-          head[cell] = (uint16_t)(idx + 1);
-        else
-          log[(size_t)(pred - 1) * E].y = (uint32_t)(idx + 1);
-      } else {
-        elem = (int)nd.x;
-        pred = cur;
-        cur = (int)nd.y;
-        have = false;
-      }
-      if (i == k1) m1 = elem;
-      if (i == k2) m2 = elem;
-    }
-    const double est = (n & 1) ? (double)m2 : __ddiv_rn((double)((long long)m1 + (long long)m2), 2.0);
-    est_maxmin(est, emx, emn);
-
-    // a6: Welford update + z-score; a7: min-max against the running z range
-    const double z = welford_update(w, est);
-    double val;
-    if (!normalize_minmax(z, w.zmax, true, w.zmin, val)) {
-      fl |= RT_FLAG_NORMALIZE;
-      val = 0.0;
-    }
-    inten[cell] = (float)val;
-    const size_t ia = (size_t)e * A + aa;
-    d.last_est[ia] = est;
-    d.last_z[ia] = z;
-    d.last_value[ia] = val;
-  }
-  double2* wp = reinterpret_cast<double2*>(d.welford + (size_t)e * 6);
-  wp[0] = make_double2(w.mean, w.m2);
-  wp[1] = make_double2(w.var, w.sd);
-  wp[2] = make_double2(w.zmax, w.zmin);
-  d.welford_n[e] = w.count;
-  reinterpret_cast<double2*>(d.est_mm)[e] = make_double2(emx, emn);
-  d.tick[e] = tick + 1;
-  if (fl) atomicOr(&d.flags[e], fl);
+#ifndef RT_STEP_MIN_CTAS
+#define RT_STEP_MIN_CTAS 4  // resident CTAs per SM ptxas must allow for (register cap = 65536 / (192 * this))
+#endif
+__global__ void __launch_bounds__(192, RT_STEP_MIN_CTAS)
+k_step(const EnvDev d, const int32_t* __restrict__ actions, int32_t* __restrict__ obs_xy,
+       int32_t* __restrict__ reward, uint8_t* __restrict__ done) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  step_tile(d, actions, obs_xy, reward, done, smem_raw);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -462,12 +506,21 @@ k_zero_maps(const EnvDev d, const uint8_t* __restrict__ mask) {
 // --------------------------------------------------------------------------------------------
 // K3: rasterise.  Vector path (cells % 8 == 0): a thread owns 8 consecutive cells of one env —
 // one 16 B load of visit counts, two 16 B loads of intensities, six 16 B streaming stores
-// (3 channels x 32 B).  A warp therefore writes 3 x 1 KB fully coalesced per pass.
-__device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
+// (3 channels x 32 B).  A warp therefore writes 3 x 1 KB fully coalesced per pass.  Almost every
+// cell of a map is unvisited, so the visit-table lookups are skipped when the 8 counts are all 0.
+__device__ __forceinline__ uint4 ld_stream_u4(const void* p) {  // read-only data of an earlier kernel
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 ld_cg_u4(const void* p) {  // data written earlier in THIS kernel: L2 only
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
   return r;
 }
 __device__ __forceinline__ void st_stream_f4(float* p, float4 v) {
@@ -475,7 +528,32 @@ __device__ __forceinline__ void st_stream_f4(float* p, float4 v) {
                : "memory");
 }
 
-template <bool kLutInSmem>
+// one 8-cell chunk; bit j of `occ` = some agent stands on cell j of the chunk
+__device__ __forceinline__ float bit_f(unsigned m, int j) { return (m >> j) & 1u ? 1.0f : 0.0f; }
+__device__ __forceinline__ void raster_chunk(float* __restrict__ o, int cells, const uint4 vv, const uint4 i0,
+                                             const uint4 i1, unsigned occ, const float* lut) {
+  st_stream_f4(o, make_float4(bit_f(occ, 0), bit_f(occ, 1), bit_f(occ, 2), bit_f(occ, 3)));
+  st_stream_f4(o + 4, make_float4(bit_f(occ, 4), bit_f(occ, 5), bit_f(occ, 6), bit_f(occ, 7)));
+  o += cells;
+  st_stream_f4(o, make_float4(__uint_as_float(i0.x), __uint_as_float(i0.y), __uint_as_float(i0.z),
+                              __uint_as_float(i0.w)));
+  st_stream_f4(o + 4, make_float4(__uint_as_float(i1.x), __uint_as_float(i1.y), __uint_as_float(i1.z),
+                                  __uint_as_float(i1.w)));
+  o += cells;
+  if ((vv.x | vv.y | vv.z | vv.w) == 0u) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    st_stream_f4(o, z);
+    st_stream_f4(o + 4, z);
+  } else {
+    st_stream_f4(o, make_float4(lut[vv.x & 0xffffu], lut[vv.x >> 16], lut[vv.y & 0xffffu], lut[vv.y >> 16]));
+    st_stream_f4(o + 4, make_float4(lut[vv.z & 0xffffu], lut[vv.z >> 16], lut[vv.w & 0xffffu], lut[vv.w >> 16]));
+  }
+}
+
+// kWithAgents = false is the "base" image used by the overlapped step: location channel all zero and
+// no read of agent_xy, so it may run concurrently with k_step; k_patch then fixes the <= A cells per env
+// that the step changed.  kUnroll chunks per thread are loaded before any is stored (bytes in flight).
+template <bool kLutInSmem, bool kWithAgents, int kUnroll>
 __global__ void __launch_bounds__(256)
 k_raster_vec(const EnvDev d, float* __restrict__ out, long long n_chunks) {
   extern __shared__ float s_lut[];
@@ -486,35 +564,66 @@ k_raster_vec(const EnvDev d, float* __restrict__ out, long long n_chunks) {
   const float* lut = kLutInSmem ? s_lut : d.lut;
   const int cpe = d.cells >> 3;  // chunks per env
   const int A = d.A, G = d.G;
+  // (env, chunk-in-env) advance incrementally: no integer division in the streaming loop
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += stride) {
-    const int e = (int)(c / cpe);
-    const int q = (int)(c - (long long)e * cpe);
-    const size_t cell0 = (size_t)e * d.cells + (size_t)q * 8;
-    const uint4 vv = ld_stream_u4(d.visit + cell0);
-    const uint4 i0 = ld_stream_u4(d.inten + cell0);
-    const uint4 i1 = ld_stream_u4(d.inten + cell0 + 4);
-    float loc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const int2* agent = reinterpret_cast<const int2*>(d.agent_xy) + (size_t)e * A;
-    for (int a = 0; a < A; ++a) {
-      const int2 p = agent[a];
-      const int rel = p.y * G + p.x - q * 8;
+  const long long c0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int e = (int)(c0 / cpe);
+  int q = (int)(c0 - (long long)e * cpe);
+  const int de = (int)(stride / cpe);
+  const int dq = (int)(stride - (long long)de * cpe);
+  for (long long c = c0; c < n_chunks; c += kUnroll * stride) {
+    uint4 vv[kUnroll], i0[kUnroll], i1[kUnroll];
+    int ee[kUnroll], qq[kUnroll];
+    bool ok[kUnroll];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (rel == j) loc[j] = 1.0f;
+    for (int u = 0; u < kUnroll; ++u) {
+      ee[u] = e;
+      qq[u] = q;
+      ok[u] = c + u * stride < n_chunks;
+      if (ok[u]) {
+        const size_t cell0 = (size_t)e * d.cells + (size_t)q * 8;
+        vv[u] = ld_stream_u4(d.visit + cell0);
+        i0[u] = ld_stream_u4(d.inten + cell0);
+        i1[u] = ld_stream_u4(d.inten + cell0 + 4);
+      }
+      e += de;
+      q += dq;
+      if (q >= cpe) {
+        q -= cpe;
+        e += 1;
+      }
     }
-    float* o = out + (size_t)e * 3 * d.cells + (size_t)q * 8;
-    st_stream_f4(o, make_float4(loc[0], loc[1], loc[2], loc[3]));
-    st_stream_f4(o + 4, make_float4(loc[4], loc[5], loc[6], loc[7]));
-    o += d.cells;
-    st_stream_f4(o, make_float4(__uint_as_float(i0.x), __uint_as_float(i0.y), __uint_as_float(i0.z),
-                                __uint_as_float(i0.w)));
-    st_stream_f4(o + 4, make_float4(__uint_as_float(i1.x), __uint_as_float(i1.y), __uint_as_float(i1.z),
-                                    __uint_as_float(i1.w)));
-    o += d.cells;
-    st_stream_f4(o, make_float4(lut[vv.x & 0xffffu], lut[vv.x >> 16], lut[vv.y & 0xffffu], lut[vv.y >> 16]));
-    st_stream_f4(o + 4, make_float4(lut[vv.z & 0xffffu], lut[vv.z >> 16], lut[vv.w & 0xffffu], lut[vv.w >> 16]));
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      if (!ok[u]) continue;
+      unsigned occ = 0u;
+      if (kWithAgents) {
+        const int2* agent = reinterpret_cast<const int2*>(d.agent_xy) + (size_t)ee[u] * A;
+        for (int a = 0; a < A; ++a) {
+          const int2 p = agent[a];
+          const unsigned r = (unsigned)(p.y * G + p.x - qq[u] * 8);
+          if (r < 8u) occ |= 1u << r;
+        }
+      }
+      raster_chunk(out + (size_t)ee[u] * 3 * d.cells + (size_t)qq[u] * 8, d.cells, vv[u], i0[u], i1[u], occ, lut);
+    }
   }
+}
+
+// After k_step and the base image: one thread per (env, agent) rewrites the agent's cell in all three
+// channels from the final map state (two agents on one cell write the same values).
+__global__ void __launch_bounds__(256)
+k_patch(const EnvDev d, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)d.E * d.A) return;
+  const int e = (int)(i / d.A);
+  const int2 p = reinterpret_cast<const int2*>(d.agent_xy)[i];
+  const int cell = p.y * d.G + p.x;
+  const size_t m = (size_t)e * d.cells + cell;
+  float* o = out + (size_t)e * 3 * d.cells + cell;
+  o[0] = 1.0f;
+  o[d.cells] = d.inten[m];
+  o[2 * (size_t)d.cells] = d.lut[d.visit[m]];
 }
 
 // Generic path for any grid side (the reference default size=10 has 100 cells): one cell per thread.

@@ -266,3 +266,36 @@ def test_sharding_invariance_global_env_ids():
         w = whole.buffer(k)
         assert torch.equal(w[:96], lo.buffer(k)) and torch.equal(w[96:], hi.buffer(k)), k
     assert torch.equal(whole.obs_maps[96:], hi.obs_maps)
+
+
+def test_overlapped_and_serial_paths_agree(monkeypatch):
+    """step() streams a base image on the auxiliary stream concurrently with k_step and patches the
+    changed cells; RT_B200_OVERLAP=0 and step(rasterize=False) + rasterize() take the serial two-kernel
+    path.  All three must produce identical tensors."""
+    import torch
+    from rad_team_b200.envs import BatchedRadSearchEnv
+
+    kw = dict(n_envs=333, n_agents=3, grid=32, max_steps=40, poly_min=1, poly_max=5, seed=15)
+    monkeypatch.setenv("RT_B200_OVERLAP", "1")
+    fused = BatchedRadSearchEnv(**kw)
+    monkeypatch.setenv("RT_B200_OVERLAP", "0")
+    monkeypatch.setenv("RT_B200_EPB", "16")
+    monkeypatch.setenv("RT_B200_RASTER_UNROLL", "4")
+    unfused = BatchedRadSearchEnv(**kw)
+    monkeypatch.delenv("RT_B200_OVERLAP")
+    monkeypatch.delenv("RT_B200_EPB")
+    monkeypatch.delenv("RT_B200_RASTER_UNROLL")
+    split = BatchedRadSearchEnv(**kw)
+    rng = np.random.default_rng(15)
+    for env in (fused, unfused, split):
+        env.reset()
+    l0 = (fused.launches, unfused.launches)
+    for t in range(40):
+        act = torch.as_tensor(rng.integers(1, 5, size=(333, 3)).astype(np.int32), device=fused.device)
+        fused.step(act); unfused.step(act)
+        split.step(act, rasterize=False); split.rasterize()
+        assert torch.equal(fused.obs_maps, unfused.obs_maps) and torch.equal(fused.obs_maps, split.obs_maps)
+        assert torch.equal(fused.reward, unfused.reward) and torch.equal(fused.obs_xy, split.obs_xy)
+    assert fused.launches - l0[0] == 120 and unfused.launches - l0[1] == 80
+    for k in ("VISIT", "INTENSITY", "WELFORD", "LOG", "HEAD"):
+        assert torch.equal(fused.buffer(k), unfused.buffer(k)) and torch.equal(fused.buffer(k), split.buffer(k)), k
