@@ -39,6 +39,10 @@ struct rt_env {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int raster_ctas = 32, raster_unroll = 2;  // full rasteriser: CTAs per SM (grid cap), chunks in flight per thread
   int base_ctas = 2, base_unroll = 4;       // base image: few resident CTAs so that k_step co-resides
+  bool base_tma = true;                     // base image through the bulk-copy engine (k_raster_base_tma)
+  int carveout = -1;                        // RT_B200_CARVEOUT=<percent shared>: common L1/shared split (A-B knob)
+  bool raster_tma = false;                  // RT_B200_RASTER_TMA=1: rasterize() = TMA base image + k_patch
+  int tma_stages = 6;
 };
 
 namespace {
@@ -120,9 +124,27 @@ void launch_raster_vec(rt_env* h, float* obs_maps, cudaStream_t st, int ctas_per
   h->launches += 1;
 }
 
+void launch_base_tma(rt_env* h, float* obs_maps, cudaStream_t st) {
+  const EnvDev& d = h->dev;
+  const int lut_n = h->lut_in_smem ? d.cap + 1 : 0;
+  const size_t smb = raster_tma_smem_bytes(d.cells, h->tma_stages, lut_n);
+  long long nb = (long long)h->n_sm * h->base_ctas;
+  if (nb > d.E) nb = d.E;
+  if (h->lut_in_smem)
+    k_raster_base_tma<true><<<(unsigned)nb, kTmaThreads, smb, st>>>(d, obs_maps, h->tma_stages);
+  else
+    k_raster_base_tma<false><<<(unsigned)nb, kTmaThreads, smb, st>>>(d, obs_maps, h->tma_stages);
+  h->launches += 1;
+}
+
 int launch_raster(rt_env* h, float* obs_maps, cudaStream_t st) {
   const EnvDev& d = h->dev;
-  if ((d.cells & 7) == 0) {
+  if ((d.cells & 7) == 0 && h->raster_tma && h->base_tma) {
+    launch_base_tma(h, obs_maps, st);
+    const long long n = (long long)d.E * d.A;
+    k_patch<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, obs_maps);
+    h->launches += 1;
+  } else if ((d.cells & 7) == 0) {
     launch_raster_vec<true>(h, obs_maps, st, h->raster_ctas, h->raster_unroll);
   } else {
     const long long n = (long long)d.E * d.cells;
@@ -146,7 +168,11 @@ int launch_step(rt_env* h, const int32_t* actions, int32_t* obs_xy, float* obs_m
     // cells per env that this step changes, and k_patch rewrites exactly those from the final state.
     RT_CUDA(cudaEventRecord(h->ev_fork, st));
     RT_CUDA(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
-    launch_raster_vec<false>(h, obs_maps, h->aux, h->base_ctas, h->base_unroll);
+    if (h->base_tma) {
+      launch_base_tma(h, obs_maps, h->aux);
+    } else {
+      launch_raster_vec<false>(h, obs_maps, h->aux, h->base_ctas, h->base_unroll);
+    }
     RT_CUDA(cudaEventRecord(h->ev_join, h->aux));
     k_step<<<blocks, epb * d.A, step_smem_bytes(epb, d.A), st>>>(d, actions, obs_xy, reward, done);
     RT_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
@@ -337,6 +363,36 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
   if (const char* ev = std::getenv("RT_B200_RASTER_UNROLL")) h->raster_unroll = std::max(1, std::atoi(ev));
   if (const char* ev = std::getenv("RT_B200_BASE_CTAS")) h->base_ctas = std::max(1, std::atoi(ev));
   if (const char* ev = std::getenv("RT_B200_BASE_UNROLL")) h->base_unroll = std::max(1, std::atoi(ev));
+  if (const char* ev = std::getenv("RT_B200_BASE_TMA")) h->base_tma = std::atoi(ev) != 0;
+  if (const char* ev = std::getenv("RT_B200_RASTER_TMA")) h->raster_tma = std::atoi(ev) != 0;
+  if (const char* ev = std::getenv("RT_B200_TMA_STAGES")) h->tma_stages = std::max(2, std::atoi(ev));
+  {
+    // the TMA ring must fit the opt-in shared memory of an SM; otherwise fall back to the LSU base image
+    const int lut_n = h->lut_in_smem ? (int)cap + 1 : 0;
+    while (h->tma_stages > 2 && raster_tma_smem_bytes((int)cells, h->tma_stages, lut_n) > 100 * 1024) h->tma_stages--;
+    const size_t smb = raster_tma_smem_bytes((int)cells, h->tma_stages, lut_n);
+    if (smb > (size_t)prop.sharedMemPerBlockOptin || (cells & 7) != 0) {
+      h->base_tma = false;
+    } else {
+      RT_CUDA_OR(cudaFuncSetAttribute(k_raster_base_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb),
+                 { rt_env_destroy(h); });
+      RT_CUDA_OR(cudaFuncSetAttribute(k_raster_base_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb),
+                 { rt_env_destroy(h); });
+    }
+  }
+  if (const char* ev = std::getenv("RT_B200_CARVEOUT")) h->carveout = std::atoi(ev);
+  if (h->carveout >= 0) {
+    // Kernels that should share an SM must agree on the L1/shared split: an SM only switches its
+    // carveout when idle, so a different preference silently serialises "concurrent" kernels.
+    const int c = h->carveout;
+    const void* fns[] = {(const void*)k_step, (const void*)k_patch,
+                         (const void*)k_raster_base_tma<true>, (const void*)k_raster_base_tma<false>,
+                         (const void*)k_raster_vec<true, false, 1>, (const void*)k_raster_vec<true, false, 2>,
+                         (const void*)k_raster_vec<true, false, 4>, (const void*)k_raster_vec<false, false, 1>,
+                         (const void*)k_raster_vec<false, false, 2>, (const void*)k_raster_vec<false, false, 4>};
+    for (const void* f : fns)
+      RT_CUDA_OR(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, c), { rt_env_destroy(h); });
+  }
   RT_CUDA_OR(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking), { rt_env_destroy(h); });
   RT_CUDA_OR(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming), { rt_env_destroy(h); });
   RT_CUDA_OR(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming), { rt_env_destroy(h); });

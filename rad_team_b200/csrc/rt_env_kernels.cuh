@@ -262,7 +262,9 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
     if (act < 1 || act > 4) atomicOr(&s.skip[le], RT_FLAG_BAD_ACTION);  // simple_gridworld.py:138
   }
 
-  // a == 0 threads own the per-env statistics; start their loads now.
+  // a == 0 threads own the per-env statistics; start their loads now.  (Packing the owners into the
+  // first warps was measured SLOWER, 0.089 vs 0.077 ms: a warp of 32 envs waits for the longest of 32
+  // list walks, a warp of ~11 envs for the longest of 11 — see profiles/r01h.)
   WelfordState w;
   double emx = 0.0, emn = 0.0, src_int = 0.0, bkg = 0.0;
   int episode = 0;
@@ -608,6 +610,105 @@ k_raster_vec(const EnvDev d, float* __restrict__ out, long long n_chunks) {
       raster_chunk(out + (size_t)ee[u] * 3 * d.cells + (size_t)qq[u] * 8, d.cells, vv[u], i0[u], i1[u], occ, lut);
     }
   }
+}
+
+// --------------------------------------------------------------------------------------------
+// K3, resource-light form for the overlapped step: the same "base" image (location = 0, intensity,
+// visit table) moved by the bulk-copy (TMA) engine instead of the LSU.  One persistent CTA of 128
+// threads per SM-slot walks envs e = blockIdx.x, + gridDim.x, ... through a ring of kStages stages:
+//     bulk g2s   intensity (4*cells B) + visit counts (2*cells B)      -> stage, mbarrier expect_tx
+//     threads    visit u16 -> table value f32 (8 cells per thread-iteration, smem to smem)
+//     bulk s2g   zero tile -> channel 0, intensity stage -> channel 1, table values -> channel 2
+// Thread 0 issues every async operation; a stage is refilled only after the bulk stores that read it
+// have finished reading (cp.async.bulk.wait_group.read).  ~256 threads and ~40 registers per SM stream
+// the whole tensor, so k_step's CTAs co-reside and their latency hides under the stream.
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int kTmaThreads = 128;
+__host__ __device__ inline size_t raster_tma_smem_bytes(int cells, int stages, int lut_entries) {
+  // [barriers 8*stages -> 128 B] [zero tile 4*cells] [stages x (inten 4*cells | visit 2*cells | table 4*cells)] [lut]
+  return 128 + (size_t)cells * 4 + (size_t)stages * cells * 10 + (size_t)lut_entries * 4;
+}
+
+template <bool kLutInSmem>
+__global__ void __launch_bounds__(kTmaThreads)
+k_raster_base_tma(const EnvDev d, float* __restrict__ out, int stages) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  const int cells = d.cells;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm);
+  float* zero = reinterpret_cast<float*>(sm + 128);
+  unsigned char* ring = sm + 128 + (size_t)cells * 4;
+  const size_t stage_bytes = (size_t)cells * 10;
+  float* s_lut = reinterpret_cast<float*>(ring + (size_t)stages * stage_bytes);
+  const int tid = threadIdx.x;
+  const uint32_t in_bytes = (uint32_t)cells * 6u, f_bytes = (uint32_t)cells * 4u;
+
+  for (int i = tid; i < cells; i += kTmaThreads) zero[i] = 0.0f;
+  if (kLutInSmem)
+    for (int i = tid; i <= d.cap; i += kTmaThreads) s_lut[i] = d.lut[i];
+  if (tid == 0)
+    for (int s = 0; s < stages; ++s) mbar_init(full + s, 1u);
+  fence_proxy_async();  // zero tile (generic writes) will be read by bulk stores
+  __syncthreads();
+  const float* lut = kLutInSmem ? s_lut : d.lut;
+
+  const int n_mine = (d.E - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // envs of this CTA
+  auto issue_load = [&](int k) {  // thread 0: env k of this CTA into stage k % stages
+    const int s = k % stages;
+    const size_t e = (size_t)blockIdx.x + (size_t)k * gridDim.x;
+    unsigned char* st = ring + (size_t)s * stage_bytes;
+    mbar_arrive_expect_tx(full + s, in_bytes);
+    bulk_g2s(st, d.inten + e * cells, f_bytes, full + s);
+    bulk_g2s(st + f_bytes, d.visit + e * cells, (uint32_t)cells * 2u, full + s);
+  };
+  if (tid == 0)
+    for (int k = 0; k < stages - 1 && k < n_mine; ++k) issue_load(k);
+
+  for (int k = 0; k < n_mine; ++k) {
+    const int s = k % stages;
+    unsigned char* st = ring + (size_t)s * stage_bytes;
+    const uint4* visit = reinterpret_cast<const uint4*>(st + f_bytes);
+    float4* table = reinterpret_cast<float4*>(st + f_bytes + (size_t)cells * 2);
+    mbar_wait(full + s, (uint32_t)((k / stages) & 1));
+    for (int i = tid; i < (cells >> 3); i += kTmaThreads) {
+      const uint4 vv = visit[i];
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if ((vv.x | vv.y | vv.z | vv.w) != 0u) {
+        a = make_float4(lut[vv.x & 0xffffu], lut[vv.x >> 16], lut[vv.y & 0xffffu], lut[vv.y >> 16]);
+        b = make_float4(lut[vv.z & 0xffffu], lut[vv.z >> 16], lut[vv.w & 0xffffu], lut[vv.w >> 16]);
+      }
+      table[2 * i] = a;
+      table[2 * i + 1] = b;
+    }
+    fence_proxy_async();  // table values (generic writes) -> visible to the bulk store
+    __syncthreads();
+    if (tid == 0) {
+      const size_t e = (size_t)blockIdx.x + (size_t)k * gridDim.x;
+      float* o = out + e * 3 * cells;
+      bulk_s2g(o, zero, f_bytes);
+      bulk_s2g(o + cells, st, f_bytes);
+      bulk_s2g(o + 2 * (size_t)cells, table, f_bytes);
+      bulk_commit();
+      // the stage that env k + stages - 1 will use is the one env k - 1 used: its stores (the group
+      // before this one) must have finished reading shared memory before it is overwritten
+      if (k + stages - 1 < n_mine) {
+        bulk_wait_read<1>();
+        issue_load(k + stages - 1);
+      }
+    }
+  }
+  if (tid == 0) bulk_wait_all();
 }
 
 // After k_step and the base image: one thread per (env, agent) rewrites the agent's cell in all three

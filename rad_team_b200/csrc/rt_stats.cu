@@ -206,15 +206,24 @@ __device__ __forceinline__ float4 ld_stream_f4(const float* p) {
   return r;
 }
 
-__device__ __forceinline__ void fold_quad(Mom& acc, const float4 v) {
-  const double a = (double)v.x, b = (double)v.y, c = (double)v.z, d = (double)v.w;
-  const double mean = ((a + b) + (c + d)) * 0.25;
-  const double da = a - mean, db = b - mean, dc = c - mean, dd = d - mean;
-  Mom q;
-  q.n = 4.0;
-  q.mean = mean;
-  q.m2 = (da * da + db * db) + (dc * dc + dd * dd);
-  acc = chan(acc, q);
+// Per-thread accumulation uses SHIFTED sums: with K = the thread's first reading, S1 = sum(x - K) and
+// S2 = sum((x - K)^2) in fp64 (five fp64 operations per reading, no divide).  K lies inside the data, so
+// M2 = S2 - S1^2/n loses at most a digit or two of fp64 — far inside the 1e-10 the tests ask for — and
+// the fp64 pipe stays well under the HBM rate.  Everything above thread level is a Chan merge.
+struct Shifted {
+  double k, s1, s2, n;
+};
+__device__ __forceinline__ void fold_one(Shifted& a, float x) {
+  const double dx = (double)x - a.k;
+  a.s1 += dx;
+  a.s2 += dx * dx;
+}
+__device__ __forceinline__ void fold_quad(Shifted& a, const float4 v) {
+  fold_one(a, v.x);
+  fold_one(a, v.y);
+  fold_one(a, v.z);
+  fold_one(a, v.w);
+  a.n += 4.0;
 }
 
 constexpr int kMomThreads = 256;
@@ -223,19 +232,27 @@ constexpr int kMomUnroll = 4;  // 16-byte loads in flight per thread
 __global__ void __launch_bounds__(kMomThreads)
 k_moments_partial(const float* __restrict__ x, long long n, double* __restrict__ partials) {
   __shared__ Mom s_w[kMomThreads / 32];
-  Mom acc = {0.0, 0.0, 0.0};
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * kMomThreads;
   long long i = (long long)blockIdx.x * kMomThreads + threadIdx.x;
+  Shifted sh = {0.0, 0.0, 0.0, 0.0};
+  if (i < n4) sh.k = (double)x[4 * i];
   for (; i + (kMomUnroll - 1) * stride < n4; i += kMomUnroll * stride) {
     float4 v[kMomUnroll];
 #pragma unroll
     for (int u = 0; u < kMomUnroll; ++u) v[u] = ld_stream_f4(x + 4 * (i + u * stride));
 #pragma unroll
-    for (int u = 0; u < kMomUnroll; ++u) fold_quad(acc, v[u]);
+    for (int u = 0; u < kMomUnroll; ++u) fold_quad(sh, v[u]);
   }
-  for (; i < n4; i += stride) fold_quad(acc, ld_stream_f4(x + 4 * i));
-  // tail (n % 4 readings): one Welford step each, by the first threads of block 0
+  for (; i < n4; i += stride) fold_quad(sh, ld_stream_f4(x + 4 * i));
+  Mom acc = {0.0, 0.0, 0.0};
+  if (sh.n > 0.0) {
+    acc.n = sh.n;
+    acc.mean = sh.k + sh.s1 / sh.n;
+    acc.m2 = sh.s2 - sh.s1 * (sh.s1 / sh.n);
+    if (acc.m2 < 0.0) acc.m2 = 0.0;
+  }
+  // tail (n % 4 readings): one single-reading merge each, by the first threads of block 0
   if (blockIdx.x == 0 && threadIdx.x < (int)(n & 3)) {
     Mom q = {1.0, (double)x[(n4 << 2) + threadIdx.x], 0.0};
     acc = chan(acc, q);
@@ -296,22 +313,34 @@ k_moments_standardize(const double* __restrict__ state, const float* __restrict_
     const double s = sqrt(m2 / (cnt - 1.0));
     sd = s > 1.0 ? s : 1.0;  // standardize.py:74
   }
+  const double inv = 1.0 / sd;  // one divide per thread; (x - mean) * inv differs from the quotient by
+                                // < 1 ulp of fp64, invisible after rounding to the fp32 output
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < n4; i += 2 * stride) {
+    const float4 v0 = ld_stream_f4(x + 4 * i), v1 = ld_stream_f4(x + 4 * (i + stride));
+    float4 o0, o1;
+    o0.x = (float)(((double)v0.x - mean) * inv); o0.y = (float)(((double)v0.y - mean) * inv);
+    o0.z = (float)(((double)v0.z - mean) * inv); o0.w = (float)(((double)v0.w - mean) * inv);
+    o1.x = (float)(((double)v1.x - mean) * inv); o1.y = (float)(((double)v1.y - mean) * inv);
+    o1.z = (float)(((double)v1.z - mean) * inv); o1.w = (float)(((double)v1.w - mean) * inv);
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(out + 4 * i), "f"(o0.x), "f"(o0.y), "f"(o0.z),
+                 "f"(o0.w) : "memory");
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(out + 4 * (i + stride)), "f"(o1.x), "f"(o1.y),
+                 "f"(o1.z), "f"(o1.w) : "memory");
+  }
+  for (; i < n4; i += stride) {
     const float4 v = ld_stream_f4(x + 4 * i);
     float4 o;
-    o.x = (float)(((double)v.x - mean) / sd);
-    o.y = (float)(((double)v.y - mean) / sd);
-    o.z = (float)(((double)v.z - mean) / sd);
-    o.w = (float)(((double)v.w - mean) / sd);
+    o.x = (float)(((double)v.x - mean) * inv); o.y = (float)(((double)v.y - mean) * inv);
+    o.z = (float)(((double)v.z - mean) * inv); o.w = (float)(((double)v.w - mean) * inv);
     asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(out + 4 * i), "f"(o.x), "f"(o.y), "f"(o.z),
-                 "f"(o.w)
-                 : "memory");
+                 "f"(o.w) : "memory");
   }
   if (blockIdx.x == 0 && threadIdx.x < (int)(n & 3)) {
     const long long j = (n4 << 2) + threadIdx.x;
-    out[j] = (float)(((double)x[j] - mean) / sd);
+    out[j] = (float)(((double)x[j] - mean) * inv);
   }
 }
 

@@ -268,7 +268,8 @@ def test_sharding_invariance_global_env_ids():
     assert torch.equal(whole.obs_maps[96:], hi.obs_maps)
 
 
-def test_overlapped_and_serial_paths_agree(monkeypatch):
+@pytest.mark.parametrize("base_tma,stages", [("1", "6"), ("1", "3"), ("0", "6")])
+def test_overlapped_and_serial_paths_agree(monkeypatch, base_tma, stages):
     """step() streams a base image on the auxiliary stream concurrently with k_step and patches the
     changed cells; RT_B200_OVERLAP=0 and step(rasterize=False) + rasterize() take the serial two-kernel
     path.  All three must produce identical tensors."""
@@ -277,6 +278,8 @@ def test_overlapped_and_serial_paths_agree(monkeypatch):
 
     kw = dict(n_envs=333, n_agents=3, grid=32, max_steps=40, poly_min=1, poly_max=5, seed=15)
     monkeypatch.setenv("RT_B200_OVERLAP", "1")
+    monkeypatch.setenv("RT_B200_BASE_TMA", base_tma)
+    monkeypatch.setenv("RT_B200_TMA_STAGES", stages)
     fused = BatchedRadSearchEnv(**kw)
     monkeypatch.setenv("RT_B200_OVERLAP", "0")
     monkeypatch.setenv("RT_B200_EPB", "16")
