@@ -275,6 +275,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- device-resident throughput ("value") -------------------------------------------------
     for _ in range(W):
         dev_step()
+    close_rollout()  # warm the rollout-close path too (first NCCL all-gather builds its channels lazily)
     barrier()
     sampler.start()
     l0 = env.launches
