@@ -125,7 +125,12 @@ typedef enum rt_buf {
   RT_BUF_VISIT_LUT = 25, /* float  [T*A+1]  BensLogNormalizer table          */
   RT_BUF_EP_RETURN = 26, /* int32  [E][A]   sum of rewards since reset       */
   RT_BUF_EP_DONE = 27,   /* uint8  [E][A]   1 once the agent has reached the source this episode */
-  RT_BUF__COUNT = 28
+  RT_BUF_SLOT = 28,      /* uint16 [E][G*G] record index of the cell + 1 (0 = not visited this episode) */
+  RT_BUF_VREC = 29,      /* uint32 [E][R][2] compact list of visited cells read by the sparse rasteriser:
+                            [0] = {n_visited, 0}; [1..2] = agent cells, 8 x uint16 (0xFFFF = none);
+                            [2+k] = {cell | visits << 16, fp32 bits of the intensity value};
+                            R = (3 + min(T*A, G*G) + 1) & ~1                                  */
+  RT_BUF__COUNT = 30
 } rt_buf;
 
 int rt_abi_version(void);

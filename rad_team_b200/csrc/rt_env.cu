@@ -34,15 +34,12 @@ struct rt_env {
   int64_t launches = 0;
   int epb = 64;
   bool lut_in_smem = true;
-  bool overlap = false;  // RT_B200_OVERLAP=1: base image on the aux stream || k_step, then k_patch (measured slower)
-  cudaStream_t aux = nullptr;  // carries the base image concurrently with k_step
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  int raster_ctas = 32, raster_unroll = 2;  // full rasteriser: CTAs per SM (grid cap), chunks in flight per thread
-  int base_ctas = 2, base_unroll = 4;       // base image: few resident CTAs so that k_step co-resides
-  bool base_tma = true;                     // base image through the bulk-copy engine (k_raster_base_tma)
-  int carveout = -1;                        // RT_B200_CARVEOUT=<percent shared>: common L1/shared split (A-B knob)
-  bool raster_tma = false;                  // RT_B200_RASTER_TMA=1: rasterize() = TMA base image + k_patch
-  int tma_stages = 6;
+  cudaStream_t aux = nullptr;  // host path: results travel back here while the rasteriser streams
+  cudaEvent_t ev_fork = nullptr;
+  int raster_ctas = 32, raster_unroll = 2;  // dense rasteriser: CTAs per SM (grid cap), chunks in flight per thread
+  bool sparse = true;                       // RT_B200_RASTER=dense selects the dense (LSU) rasteriser
+  int sparse_ctas = 1;                      // sparse rasteriser: persistent CTAs (8 warp pipelines each) per SM
+  int sparse_hints = 3;                     // bit 0: evict-first bulk stores, bit 1: evict-last record loads
 };
 
 namespace {
@@ -91,6 +88,14 @@ k_episode_stats(const int32_t* __restrict__ ep_return, const uint8_t* __restrict
   }
 }
 
+__global__ void k_init_headers(uint2* __restrict__ vrec, int E, int stride) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  vrec[(size_t)e * stride + 0] = make_uint2(0u, 0u);
+  vrec[(size_t)e * stride + 1] = make_uint2(0xffffffffu, 0xffffffffu);
+  vrec[(size_t)e * stride + 2] = make_uint2(0xffffffffu, 0xffffffffu);
+}
+
 __global__ void k_or_flags(const int32_t* __restrict__ flags, int n, int32_t* __restrict__ out) {
   int v = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v |= flags[i];
@@ -98,61 +103,49 @@ __global__ void k_or_flags(const int32_t* __restrict__ flags, int n, int32_t* __
   if ((threadIdx.x & 31) == 0 && v) atomicOr(out, v);
 }
 
-template <bool kAgents>
-void launch_raster_vec(rt_env* h, float* obs_maps, cudaStream_t st, int ctas_per_sm, int unroll) {
+void launch_raster_vec(rt_env* h, float* obs_maps, cudaStream_t st) {
   const EnvDev& d = h->dev;
   const long long n_chunks = (long long)d.E * (d.cells >> 3);
   const int threads = 256;
   long long blocks = (n_chunks + threads - 1) / threads;
-  const long long cap_blocks = (long long)h->n_sm * ctas_per_sm;
+  const long long cap_blocks = (long long)h->n_sm * h->raster_ctas;
   if (blocks > cap_blocks) blocks = cap_blocks;
   const size_t sm = h->lut_in_smem ? (size_t)(d.cap + 1) * 4 : 0;
-#define RT_LAUNCH_RV(U)                                                                                  \
-  do {                                                                                                   \
-    if (h->lut_in_smem)                                                                                  \
-      k_raster_vec<true, kAgents, U><<<(unsigned)blocks, threads, sm, st>>>(d, obs_maps, n_chunks);     \
-    else                                                                                                 \
-      k_raster_vec<false, kAgents, U><<<(unsigned)blocks, threads, 0, st>>>(d, obs_maps, n_chunks);     \
+#define RT_LAUNCH_RV(U)                                                                       \
+  do {                                                                                        \
+    if (h->lut_in_smem)                                                                       \
+      k_raster_vec<true, U><<<(unsigned)blocks, threads, sm, st>>>(d, obs_maps, n_chunks);   \
+    else                                                                                      \
+      k_raster_vec<false, U><<<(unsigned)blocks, threads, 0, st>>>(d, obs_maps, n_chunks);   \
   } while (0)
-  if (unroll >= 4)
+  if (h->raster_unroll >= 4)
     RT_LAUNCH_RV(4);
-  else if (unroll >= 2)
+  else if (h->raster_unroll >= 2)
     RT_LAUNCH_RV(2);
   else
     RT_LAUNCH_RV(1);
 #undef RT_LAUNCH_RV
-  h->launches += 1;
-}
-
-void launch_base_tma(rt_env* h, float* obs_maps, cudaStream_t st) {
-  const EnvDev& d = h->dev;
-  const int lut_n = h->lut_in_smem ? d.cap + 1 : 0;
-  const size_t smb = raster_tma_smem_bytes(d.cells, h->tma_stages, lut_n);
-  long long nb = (long long)h->n_sm * h->base_ctas;
-  if (nb > d.E) nb = d.E;
-  if (h->lut_in_smem)
-    k_raster_base_tma<true><<<(unsigned)nb, kTmaThreads, smb, st>>>(d, obs_maps, h->tma_stages);
-  else
-    k_raster_base_tma<false><<<(unsigned)nb, kTmaThreads, smb, st>>>(d, obs_maps, h->tma_stages);
-  h->launches += 1;
 }
 
 int launch_raster(rt_env* h, float* obs_maps, cudaStream_t st) {
   const EnvDev& d = h->dev;
-  if ((d.cells & 7) == 0 && h->raster_tma && h->base_tma) {
-    launch_base_tma(h, obs_maps, st);
-    const long long n = (long long)d.E * d.A;
-    k_patch<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, obs_maps);
-    h->launches += 1;
+  if (h->sparse) {
+    const size_t smb = raster_sparse_smem_bytes(d.cells, d.rec_prefix, h->lut_in_smem ? d.cap + 1 : 0);
+    long long nb = (long long)h->n_sm * h->sparse_ctas;
+    if (nb * kSpWarps > d.E) nb = (d.E + kSpWarps - 1) / kSpWarps;
+    if (h->lut_in_smem)
+      k_raster_sparse<true><<<(unsigned)nb, kSpThreads, smb, st>>>(d, obs_maps, h->sparse_hints);
+    else
+      k_raster_sparse<false><<<(unsigned)nb, kSpThreads, smb, st>>>(d, obs_maps, h->sparse_hints);
   } else if ((d.cells & 7) == 0) {
-    launch_raster_vec<true>(h, obs_maps, st, h->raster_ctas, h->raster_unroll);
+    launch_raster_vec(h, obs_maps, st);
   } else {
     const long long n = (long long)d.E * d.cells;
     long long blocks = (n + 255) / 256;
     if (blocks > (long long)h->n_sm * 32) blocks = (long long)h->n_sm * 32;
     k_raster_any<<<(unsigned)blocks, 256, 0, st>>>(d, obs_maps, n);
-    h->launches += 1;
   }
+  h->launches += 1;
   RT_CUDA_LAUNCH_CHECK();
   return RT_OK;
 }
@@ -162,26 +155,6 @@ int launch_step(rt_env* h, const int32_t* actions, int32_t* obs_xy, float* obs_m
   const EnvDev& d = h->dev;
   const int epb = h->epb;
   const unsigned blocks = (unsigned)((d.E + epb - 1) / epb);
-  if (obs_maps && (d.cells & 7) == 0 && h->overlap) {
-    // Overlapped step: the base image (location = 0, intensity / visit maps as they stand) streams on
-    // the auxiliary stream WHILE k_step runs on the caller's stream; the two only race on the <= A
-    // cells per env that this step changes, and k_patch rewrites exactly those from the final state.
-    RT_CUDA(cudaEventRecord(h->ev_fork, st));
-    RT_CUDA(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
-    if (h->base_tma) {
-      launch_base_tma(h, obs_maps, h->aux);
-    } else {
-      launch_raster_vec<false>(h, obs_maps, h->aux, h->base_ctas, h->base_unroll);
-    }
-    RT_CUDA(cudaEventRecord(h->ev_join, h->aux));
-    k_step<<<blocks, epb * d.A, step_smem_bytes(epb, d.A), st>>>(d, actions, obs_xy, reward, done);
-    RT_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
-    const long long n = (long long)d.E * d.A;
-    k_patch<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, obs_maps);
-    h->launches += 2;
-    RT_CUDA_LAUNCH_CHECK();
-    return RT_OK;
-  }
   k_step<<<blocks, epb * d.A, step_smem_bytes(epb, d.A), st>>>(d, actions, obs_xy, reward, done);
   h->launches += 1;
   RT_CUDA_LAUNCH_CHECK();
@@ -243,6 +216,9 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
 
   const size_t E = (size_t)cfg->n_envs, A = (size_t)cfg->n_agents;
   const size_t cells = (size_t)cfg->grid * cfg->grid;
+  // visited-cell records: 3 header slots + one record per distinct visited cell, rounded up to even
+  const size_t max_rec = (size_t)cap < cells ? (size_t)cap : cells;
+  const int rec_stride = (int)((3 + max_rec + 1) & ~(size_t)1);
   const size_t sz[RT_BUF__COUNT] = {
       /*AGENT_XY*/ E * A * 8,   /*PREV_DIST*/ E * A * 4, /*START_XY*/ E * A * 8, /*SRC_XY*/ E * 8,
       /*SRC_INT*/ E * 8,        /*BKG*/ E * 8,           /*N_POLY*/ E * 4,       /*EDGES*/ E * RT_MAX_EDGES * 16,
@@ -251,7 +227,7 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
       /*WELFORD_N*/ E * 4,      /*EST_MAXMIN*/ E * 16,   /*FLAGS*/ E * 4,        /*LAST_COUNT*/ E * A * 4,
       /*LAST_LOS*/ E * A,       /*LAST_LAMBDA*/ E * A * 8, /*LAST_EST*/ E * A * 8, /*LAST_Z*/ E * A * 8,
       /*LAST_VALUE*/ E * A * 8, /*VISIT_LUT*/ ((size_t)cap + 1) * 4, /*EP_RETURN*/ E * A * 4,
-      /*EP_DONE*/ E * A};
+      /*EP_DONE*/ E * A,        /*SLOT*/ E * cells * 2,  /*VREC*/ E * (size_t)rec_stride * 8};
   Carver cv;
   size_t off[RT_BUF__COUNT];
   for (int i = 0; i < RT_BUF__COUNT; ++i) off[i] = cv.take(sz[i]);
@@ -319,10 +295,17 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
   d.lut = (float*)h->buf_ptr[RT_BUF_VISIT_LUT];
   d.ep_return = (int32_t*)h->buf_ptr[RT_BUF_EP_RETURN];
   d.ep_done = (uint8_t*)h->buf_ptr[RT_BUF_EP_DONE];
+  d.slot = (uint16_t*)h->buf_ptr[RT_BUF_SLOT];
+  d.vrec = (uint2*)h->buf_ptr[RT_BUF_VREC];
+  d.rec_stride = rec_stride;
+  d.rec_prefix = rec_stride < 128 ? rec_stride : 128;  // 1 KB per env covers 125 visited cells; the rest is read directly
   d.rollout = nullptr;
   d.inj = nullptr;
   d.inj_k = 0;
 
+  // record headers before the first reset: no visited cells, no agents
+  k_init_headers<<<(unsigned)((E + 255) / 256), 256>>>(d.vrec, (int)E, rec_stride);
+  RT_CUDA_OR(cudaGetLastError(), { rt_env_destroy(h); });
   // episode counters start at -1 so the first reset opens episode 0; Welford std starts at 1
   {
     std::vector<int32_t> ep(E, -1);
@@ -350,7 +333,7 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
   h->lut_in_smem = ((size_t)cap + 1) * 4 <= 32 * 1024;
   // envs per CTA of k_step: <= 192 threads, and enough CTAs to cover the SMs twice when E allows
   int epb = 192 / cfg->n_agents;
-  if (epb > 64) epb = 64;
+  if (epb > 32) epb = 32;  // measured: 32 envs per CTA beats 64 and 16 at c3 (profiles/r01m)
   while (epb > 8 && (cfg->n_envs + epb - 1) / epb < 2 * h->n_sm) epb >>= 1;
   if (epb * cfg->n_agents < 32) epb = (32 + cfg->n_agents - 1) / cfg->n_agents;
   h->epb = epb;
@@ -358,44 +341,26 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
     const int v = std::atoi(ev);
     if (v >= 1 && v * cfg->n_agents <= 192) h->epb = v;
   }
-  if (const char* ev = std::getenv("RT_B200_OVERLAP")) h->overlap = std::atoi(ev) != 0;
   if (const char* ev = std::getenv("RT_B200_RASTER_CTAS")) h->raster_ctas = std::max(1, std::atoi(ev));
   if (const char* ev = std::getenv("RT_B200_RASTER_UNROLL")) h->raster_unroll = std::max(1, std::atoi(ev));
-  if (const char* ev = std::getenv("RT_B200_BASE_CTAS")) h->base_ctas = std::max(1, std::atoi(ev));
-  if (const char* ev = std::getenv("RT_B200_BASE_UNROLL")) h->base_unroll = std::max(1, std::atoi(ev));
-  if (const char* ev = std::getenv("RT_B200_BASE_TMA")) h->base_tma = std::atoi(ev) != 0;
-  if (const char* ev = std::getenv("RT_B200_RASTER_TMA")) h->raster_tma = std::atoi(ev) != 0;
-  if (const char* ev = std::getenv("RT_B200_TMA_STAGES")) h->tma_stages = std::max(2, std::atoi(ev));
+  if (const char* ev = std::getenv("RT_B200_SPARSE_CTAS")) h->sparse_ctas = std::max(1, std::atoi(ev));
+  if (const char* ev = std::getenv("RT_B200_SPARSE_HINTS")) h->sparse_hints = std::atoi(ev);
+  if (const char* ev = std::getenv("RT_B200_RASTER")) h->sparse = std::strcmp(ev, "dense") != 0;
   {
-    // the TMA ring must fit the opt-in shared memory of an SM; otherwise fall back to the LSU base image
-    const int lut_n = h->lut_in_smem ? (int)cap + 1 : 0;
-    while (h->tma_stages > 2 && raster_tma_smem_bytes((int)cells, h->tma_stages, lut_n) > 100 * 1024) h->tma_stages--;
-    const size_t smb = raster_tma_smem_bytes((int)cells, h->tma_stages, lut_n);
-    if (smb > (size_t)prop.sharedMemPerBlockOptin || (cells & 7) != 0) {
-      h->base_tma = false;
+    // the sparse rasteriser composes whole [3][G][G] tiles in shared memory: needs cells % 8 == 0, cell
+    // indices that fit 16 bits and kSpStages tiles within the opt-in shared memory; otherwise dense
+    const size_t smb = raster_sparse_smem_bytes((int)cells, d.rec_prefix, h->lut_in_smem ? (int)cap + 1 : 0);
+    if ((cells & 7) != 0 || cells > 65535 || smb > (size_t)prop.sharedMemPerBlockOptin) {
+      h->sparse = false;
     } else {
-      RT_CUDA_OR(cudaFuncSetAttribute(k_raster_base_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb),
+      RT_CUDA_OR(cudaFuncSetAttribute(k_raster_sparse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb),
                  { rt_env_destroy(h); });
-      RT_CUDA_OR(cudaFuncSetAttribute(k_raster_base_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb),
+      RT_CUDA_OR(cudaFuncSetAttribute(k_raster_sparse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb),
                  { rt_env_destroy(h); });
     }
   }
-  if (const char* ev = std::getenv("RT_B200_CARVEOUT")) h->carveout = std::atoi(ev);
-  if (h->carveout >= 0) {
-    // Kernels that should share an SM must agree on the L1/shared split: an SM only switches its
-    // carveout when idle, so a different preference silently serialises "concurrent" kernels.
-    const int c = h->carveout;
-    const void* fns[] = {(const void*)k_step, (const void*)k_patch,
-                         (const void*)k_raster_base_tma<true>, (const void*)k_raster_base_tma<false>,
-                         (const void*)k_raster_vec<true, false, 1>, (const void*)k_raster_vec<true, false, 2>,
-                         (const void*)k_raster_vec<true, false, 4>, (const void*)k_raster_vec<false, false, 1>,
-                         (const void*)k_raster_vec<false, false, 2>, (const void*)k_raster_vec<false, false, 4>};
-    for (const void* f : fns)
-      RT_CUDA_OR(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, c), { rt_env_destroy(h); });
-  }
   RT_CUDA_OR(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking), { rt_env_destroy(h); });
   RT_CUDA_OR(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming), { rt_env_destroy(h); });
-  RT_CUDA_OR(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming), { rt_env_destroy(h); });
   *out = h;
   return RT_OK;
 }
@@ -407,7 +372,6 @@ int rt_env_destroy(rt_env* h) {
     cudaStreamDestroy(h->aux);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->slab) cudaFree(h->slab);
   if (h->pinned) cudaFreeHost(h->pinned);
   delete h;

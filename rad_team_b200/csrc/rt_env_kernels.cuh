@@ -36,6 +36,12 @@ struct EnvDev {
   uint16_t* visit;  // [E][cells]
   float* inten;     // [E][cells]
   uint16_t* head;   // [E][cells]  smallest log entry of the cell, +1 (0 = empty)
+  uint16_t* slot;   // [E][cells]  record index of the cell in vrec, +1 (0 = never visited this episode)
+  uint2* vrec;      // [E][rec_stride]  compact list of the VISITED cells, what the sparse rasteriser reads:
+                    //   [0] = {n_visited, 0}; [1..2] = the agents' cells, 8 x uint16 (0xFFFF = none);
+                    //   [2 + k] = {cell | visits << 16, fp32 bits of the intensity value}, k = 1..n_visited
+  int rec_stride;   // uint2 per env (even)
+  int rec_prefix;   // uint2 per env moved by the rasteriser's bulk copy (<= rec_stride, even)
   uint2* log;       // [cap][E]    {count, next larger entry of the same cell + 1}
   double* welford;  // [E][6]
   int32_t* welford_n;
@@ -102,83 +108,90 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 constexpr int kEdgeRowF4 = RT_MAX_EDGES + 1;  // 21 float4 = 336 B rows: conflict-free float4 reads
 
 struct StepSmem {  // carved from dynamic shared memory, see step_smem_bytes()
+  uint64_t* bar;
   float4* edges;   // [epb][kEdgeRowF4]
+  double* est;     // [epb*A]  median estimate computed by the agent's own thread
   int* n_poly;     // [epb]
   int* skip;       // [epb]  RT_FLAG_* that void this env's step
   int* eflags;     // [epb]  flags raised by the agents' samplers
-  int* cell;       // [epb*A]
-  int* count;      // [epb*A]
-  int* pre_vh;     // [epb*A]  prefetched visit count | head << 16 of the agent's new cell
-  uint2* pre_node; // [epb*A]  prefetched first (smallest) log entry of that cell
-  uint64_t* bar;
+  int* cell;       // [epb*A]  the agent's cell after the move
+  int* count;      // [epb*A]  Poisson count
+  int* slot;       // [epb*A]  prefetched record slot of the cell (0 = none yet)
+  int* nread;      // [epb*A]  readings at the cell incl. this one; 0 = deferred to the owner (cell clash)
 };
 __host__ __device__ inline size_t step_smem_bytes(int epb, int A) {
   return 16 + (size_t)epb * kEdgeRowF4 * 16 + (size_t)epb * A * 8 + (size_t)epb * 3 * 4 +
-         (size_t)epb * A * 3 * 4;
+         (size_t)epb * A * 4 * 4;
 }
 
-// K4a: the env's agents feed ONE estimator / Welford / normaliser, in agent order (one thread per env).
+// a9: IntensityResamplingEstimator.update + get_estimate (estimator.py:31-48,61-70) for one cell.
+// The cell's readings form a linked list sorted by value (head = smallest; log entry = {count, next+1});
+// insert reading `cnt` as entry `idx` and pick the median — elements (n-1)/2 and n/2 of the NEW list of
+// n readings — in the same walk.  `cur` = list head (+1, 0 = empty); (nd, have) = an already loaded head.
+__device__ __forceinline__ double list_insert_median(uint2* __restrict__ log, size_t E, uint16_t* head_cell,
+                                                     int idx, int cnt, int n, int cur, uint2 nd, bool have) {
+  const int k1 = (n - 1) >> 1, k2 = n >> 1;
+  int pred = 0, m1 = 0, m2 = 0;
+  bool inserted = false;
+  for (int i = 0; i <= k2 || !inserted; ++i) {
+    if (cur != 0 && !have) {
+      nd = log[(size_t)(cur - 1) * E];
+      have = true;
+    }
+    int elem;
+    if (!inserted && (cur == 0 || (int)nd.x > cnt)) {
+      elem = cnt;
+      inserted = true;
+      log[(size_t)idx * E] = make_uint2((uint32_t)cnt, (uint32_t)cur);
+      if (pred == 0)
+        *head_cell = (uint16_t)(idx + 1);
+      else
+        log[(size_t)(pred - 1) * E].y = (uint32_t)(idx + 1);
+    } else {
+      elem = (int)nd.x;
+      pred = cur;
+      cur = (int)nd.y;
+      have = false;
+    }
+    if (i == k1) m1 = elem;
+    if (i == k2) m2 = elem;
+  }
+  // statistics.median: middle element, or the mean of the middle two
+  return (n & 1) ? (double)m2 : __ddiv_rn((double)((long long)m1 + (long long)m2), 2.0);
+}
+
+// K4a: the env's agents feed ONE Welford standardiser / normaliser, in agent order (one thread per env).
+// The per-cell estimator work was already done in parallel by the agents' own threads, except for agents
+// whose cell was also entered by an earlier agent of the env in this very step (nread == 0): those are
+// replayed here, in order, against the updated list.
 __device__ __forceinline__ void stats_chain(const EnvDev& d, const StepSmem& s, int e, int le, int tick,
-                                            WelfordState& w, double emx, double emn) {
+                                            WelfordState& w, double emx, double emn, int nv) {
   const int A = d.A;
   uint16_t* visit = d.visit + (size_t)e * d.cells;
   uint16_t* head = d.head + (size_t)e * d.cells;
+  uint16_t* slot = d.slot + (size_t)e * d.cells;
+  uint2* rec = d.vrec + (size_t)e * d.rec_stride;
   float* inten = d.inten + (size_t)e * d.cells;
-  uint2* log = d.log + e;  // entry i at log[i * E]
-  const size_t E = (size_t)d.E;
   int fl = s.eflags[le];
   for (int aa = 0; aa < A; ++aa) {
-    const int cell = s.cell[le * A + aa];
-    const int cnt = s.count[le * A + aa];
-    const int idx = tick * A + aa;
-    bool clash = false;  // an earlier agent of this env wrote this cell in this very step
-    for (int bb = 0; bb < aa; ++bb) clash |= s.cell[le * A + bb] == cell;
-    int n, cur;  // readings at this cell including this one; list cursor (entry + 1, 0 = end)
-    uint2 nd = make_uint2(0u, 0u);
-    bool have = false;
-    if (!clash) {
-      const unsigned vh = (unsigned)s.pre_vh[le * A + aa];
-      n = (int)(vh & 0xffffu) + 1;
-      cur = (int)(vh >> 16);
-      nd = s.pre_node[le * A + aa];
-      have = cur != 0;
+    const int i = le * A + aa;
+    const int cell = s.cell[i];
+    int n = s.nread[i], sl;
+    double est;
+    if (n != 0) {
+      est = s.est[i];
+      sl = s.slot[i];
     } else {
       n = (int)visit[cell] + 1;
-      cur = (int)head[cell];
+      visit[cell] = (uint16_t)n;
+      est = list_insert_median(d.log + e, (size_t)d.E, head + cell, tick * A + aa, s.count[i], n, (int)head[cell],
+                               make_uint2(0u, 0u), false);
+      sl = (int)slot[cell];
     }
-    visit[cell] = (uint16_t)n;
-
-    // a9: IntensityResamplingEstimator.update + get_estimate (estimator.py:31-48,61-70).
-    // The cell's readings form a linked list sorted by value; insert the new reading and
-    // pick the median (elements (n-1)/2 and n/2 of the new list) in the same walk.
-    const int k1 = (n - 1) >> 1, k2 = n >> 1;
-    int pred = 0;
-    bool inserted = false;
-    int m1 = 0, m2 = 0;
-    for (int i = 0; i <= k2 || !inserted; ++i) {
-      if (cur != 0 && !have) {
-        nd = log[(size_t)(cur - 1) * E];
-        have = true;
-      }
-      int elem;
-      if (!inserted && (cur == 0 || (int)nd.x > cnt)) {
-        elem = cnt;
-        inserted = true;
-        log[(size_t)idx * E] = make_uint2((uint32_t)cnt, (uint32_t)cur);
-        if (pred == 0)
-          head[cell] = (uint16_t)(idx + 1);
-        else
-          log[(size_t)(pred - 1) * E].y = (uint32_t)(idx + 1);
-      } else {
-        elem = (int)nd.x;
-        pred = cur;
-        cur = (int)nd.y;
-        have = false;
-      }
-      if (i == k1) m1 = elem;
-      if (i == k2) m2 = elem;
+    if (sl == 0) {  // first visit of this cell in the episode: open a record
+      sl = ++nv;
+      slot[cell] = (uint16_t)sl;
     }
-    const double est = (n & 1) ? (double)m2 : __ddiv_rn((double)((long long)m1 + (long long)m2), 2.0);
     est_maxmin(est, emx, emn);
 
     // a6: Welford update + z-score; a7: min-max against the running z range
@@ -189,6 +202,7 @@ __device__ __forceinline__ void stats_chain(const EnvDev& d, const StepSmem& s, 
       val = 0.0;
     }
     inten[cell] = (float)val;
+    rec[2 + sl] = make_uint2((uint32_t)cell | ((uint32_t)n << 16), __float_as_uint((float)val));
     const size_t ia = (size_t)e * A + aa;
     d.last_est[ia] = est;
     d.last_z[ia] = z;
@@ -202,6 +216,19 @@ __device__ __forceinline__ void stats_chain(const EnvDev& d, const StepSmem& s, 
   reinterpret_cast<double2*>(d.est_mm)[e] = make_double2(emx, emn);
   d.tick[e] = tick + 1;
   if (fl) atomicOr(&d.flags[e], fl);
+  // record header: number of visited cells and where the agents stand now
+  unsigned long long p0 = ~0ull, p1 = ~0ull;  // 8 x uint16 agent cells, 0xFFFF = no agent
+  for (int aa = 0; aa < A; ++aa) {
+    const unsigned long long c = (unsigned long long)(s.cell[le * A + aa] & 0xffff);
+    const int sh = 16 * (aa & 3);
+    if (aa < 4)
+      p0 = (p0 & ~(0xffffull << sh)) | (c << sh);
+    else
+      p1 = (p1 & ~(0xffffull << sh)) | (c << sh);
+  }
+  rec[0] = make_uint2((uint32_t)nv, 0u);
+  rec[1] = make_uint2((uint32_t)p0, (uint32_t)(p0 >> 32));
+  rec[2] = make_uint2((uint32_t)p1, (uint32_t)(p1 >> 32));
 }
 
 __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __restrict__ actions,
@@ -212,13 +239,14 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
   StepSmem s;
   s.bar = reinterpret_cast<uint64_t*>(smem_raw);
   s.edges = reinterpret_cast<float4*>(smem_raw + 16);
-  s.pre_node = reinterpret_cast<uint2*>(smem_raw + 16 + (size_t)epb * kEdgeRowF4 * 16);
-  s.n_poly = reinterpret_cast<int*>(s.pre_node + epb * A);
+  s.est = reinterpret_cast<double*>(smem_raw + 16 + (size_t)epb * kEdgeRowF4 * 16);
+  s.n_poly = reinterpret_cast<int*>(s.est + epb * A);
   s.skip = s.n_poly + epb;
   s.eflags = s.skip + epb;
   s.cell = s.eflags + epb;
   s.count = s.cell + epb * A;
-  s.pre_vh = s.count + epb * A;
+  s.slot = s.count + epb * A;
+  s.nread = s.slot + epb * A;
 
   const int t = threadIdx.x;
   const int le = t / A;
@@ -263,11 +291,10 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
   }
 
   // a == 0 threads own the per-env statistics; start their loads now.  (Packing the owners into the
-  // first warps was measured SLOWER, 0.089 vs 0.077 ms: a warp of 32 envs waits for the longest of 32
-  // list walks, a warp of ~11 envs for the longest of 11 — see profiles/r01h.)
+  // first warps was measured SLOWER, 0.089 vs 0.077 ms — see profiles/r01h.)
   WelfordState w;
   double emx = 0.0, emn = 0.0, src_int = 0.0, bkg = 0.0;
-  int episode = 0;
+  int episode = 0, nv = 0;
   if (valid) {
     src_int = d.src_int[e];
     bkg = d.bkg[e];
@@ -280,28 +307,32 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
       const double2 mm = reinterpret_cast<const double2*>(d.est_mm)[e];
       emx = mm.x;
       emn = mm.y;
+      nv = (int)d.vrec[(size_t)e * d.rec_stride].x;
     }
   }
 
   mbar_wait(s.bar, 0);  // geometry of every env of this CTA has landed in shared memory
   __syncthreads();      // skip flags complete
 
+  // ---- K1: motion, collision, reward (one thread per agent) ------------------------------------
   const int skip = valid ? s.skip[le] : 0;
+  const bool live = valid && !skip;
+  const size_t ia = (size_t)e * A + a;
+  const float4* my_edges = s.edges + (size_t)le * kEdgeRowF4;
+  int nx = pos.x, ny = pos.y, cell = 0;
+  unsigned pv = 0u, ph = 0u, psl = 0u;
   if (valid) {
-    const size_t ia = (size_t)e * A + a;
     if (skip) {  // reference raises before touching state: report the unchanged position
       reinterpret_cast<int2*>(obs_xy)[ia] = pos;
       reward[ia] = 0;
       done[ia] = 0;
-      s.cell[t] = pos.y * d.G + pos.x;
     } else {
-      const float4* my_edges = s.edges + (size_t)le * kEdgeRowF4;
       np = s.n_poly[le];
       // a4: agent = clip(agent + direction, 0, size-1)   (simple_gridworld.py:26-31,141)
       const int dx = (act == 2) - (act == 3);
       const int dy = (act == 1) - (act == 4);
-      int nx = min(max(pos.x + dx, 0), d.G - 1);
-      int ny = min(max(pos.y + dy, 0), d.G - 1);
+      nx = min(max(pos.x + dx, 0), d.G - 1);
+      ny = min(max(pos.y + dy, 0), d.G - 1);
       // N4: refuse a move whose centre-to-centre path crosses an obstruction edge
       if ((nx != pos.x || ny != pos.y) && np > 0 &&
           polys_crossed(my_edges, np, (float)pos.x + 0.5f, (float)pos.y + 0.5f, (float)nx + 0.5f,
@@ -320,56 +351,73 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
       done[ia] = dn ? 1 : 0;
       d.ep_return[ia] += rw;
       if (dn) d.ep_done[ia] = 1;
-
-      // Prefetch what the per-env statistics chain will need for this cell (visit count, list head,
-      // first list entry): the loads fly while the line-of-sight tests and the sampler compute.
-      const int cell = ny * d.G + nx;
+    }
+    cell = ny * d.G + nx;
+    s.cell[t] = cell;
+    if (live) {  // cell state for the estimator: the loads fly while line of sight and sampler compute
       const size_t mcell = (size_t)e * d.cells + cell;
-      const unsigned pv = d.visit[mcell];
-      const unsigned ph = d.head[mcell];
-
-      // N2 + N1: obstructions on the line of sight, expected count
-      const int nb = np > 0 ? polys_crossed(my_edges, np, (float)nx + 0.5f, (float)ny + 0.5f,
-                                            (float)src.x + 0.5f, (float)src.y + 0.5f)
-                            : 0;
-      const int ddx = nx - src.x, ddy = ny - src.y;
-      double d2 = __dmul_rn((double)(ddx * ddx + ddy * ddy), d.pitch2);
-      if (d2 < d.dmin2) d2 = d.dmin2;
-      double strength = src_int;
-      for (int i = 0; i < nb; ++i) strength = __dmul_rn(strength, d.transmission);
-      const double lam = __dadd_rn(__ddiv_rn(strength, d2), bkg);
-
-      uint2 pnode = make_uint2(0u, 0u);
-      if (ph != 0u) pnode = d.log[(size_t)(ph - 1) * d.E + e];
-
-      // N3: Poisson count
-      Draws dr;
-      dr.init(d.seed, d.gid_base + e, STREAM_MEASURE, a, tick, episode);
-      if (d.inj != nullptr) {
-        dr.inj = d.inj + ((size_t)e * A + a) * (size_t)d.inj_k;
-        dr.inj_k = d.inj_k;
-      }
-      int fl = 0;
-      const long long cnt = poisson_draw(lam, dr, fl);
-      if (fl) atomicOr(&s.eflags[le], fl);
-
-      s.cell[t] = cell;
-      s.count[t] = (int)cnt;
-      s.pre_vh[t] = (int)(pv | (ph << 16));
-      s.pre_node[t] = pnode;
-      d.last_count[ia] = (int)cnt;
-      if (d.rollout != nullptr) d.rollout[((size_t)tick * d.E + e) * A + a] = (float)cnt;
-      d.last_los[ia] = (uint8_t)nb;
-      d.last_lambda[ia] = lam;
+      pv = d.visit[mcell];
+      ph = d.head[mcell];
+      psl = d.slot[mcell];
     }
   }
-  __syncthreads();  // readings of all agents are in shared memory
+  __syncthreads();  // every agent's new cell is known to its env-mates
 
+  // ---- K2: measurement, then the agent's own estimator update ------------------------------------
+  if (live) {
+    bool clash = false;  // an earlier agent of this env entered the same cell in this very step
+    for (int bb = 0; bb < a; ++bb) clash |= s.cell[le * A + bb] == cell;
+    // N2 + N1: obstructions on the line of sight, expected count
+    const int nb = np > 0 ? polys_crossed(my_edges, np, (float)nx + 0.5f, (float)ny + 0.5f,
+                                          (float)src.x + 0.5f, (float)src.y + 0.5f)
+                          : 0;
+    const int ddx = nx - src.x, ddy = ny - src.y;
+    double d2 = __dmul_rn((double)(ddx * ddx + ddy * ddy), d.pitch2);
+    if (d2 < d.dmin2) d2 = d.dmin2;
+    double strength = src_int;
+    for (int i = 0; i < nb; ++i) strength = __dmul_rn(strength, d.transmission);
+    const double lam = __dadd_rn(__ddiv_rn(strength, d2), bkg);
+
+    uint2 pnode = make_uint2(0u, 0u);
+    if (!clash && ph != 0u) pnode = d.log[(size_t)(ph - 1) * d.E + e];
+
+    // N3: Poisson count
+    Draws dr;
+    dr.init(d.seed, d.gid_base + e, STREAM_MEASURE, a, tick, episode);
+    if (d.inj != nullptr) {
+      dr.inj = d.inj + ((size_t)e * A + a) * (size_t)d.inj_k;
+      dr.inj_k = d.inj_k;
+    }
+    int fl = 0;
+    const long long cnt = poisson_draw(lam, dr, fl);
+    if (fl) atomicOr(&s.eflags[le], fl);
+
+    // a9 in parallel across the env's agents (different cells => independent lists)
+    int n = 0;
+    double est = 0.0;
+    if (!clash) {
+      n = (int)pv + 1;
+      d.visit[(size_t)e * d.cells + cell] = (uint16_t)n;
+      est = list_insert_median(d.log + e, (size_t)d.E, d.head + (size_t)e * d.cells + cell, tick * A + a, (int)cnt,
+                               n, (int)ph, pnode, ph != 0u);
+    }
+    s.count[t] = (int)cnt;
+    s.slot[t] = (int)psl;
+    s.nread[t] = n;
+    s.est[t] = est;
+    d.last_count[ia] = (int)cnt;
+    if (d.rollout != nullptr) d.rollout[((size_t)tick * d.E + e) * A + a] = (float)cnt;
+    d.last_los[ia] = (uint8_t)nb;
+    d.last_lambda[ia] = lam;
+  }
+  __syncthreads();  // readings and estimates of all agents are in shared memory
+
+  // ---- K4a: the env's sequential statistics -------------------------------------------------------
   if (valid && a == 0) {
     if (skip)
       atomicOr(&d.flags[e], skip);
     else
-      stats_chain(d, s, e, le, tick, w, emx, emn);
+      stats_chain(d, s, e, le, tick, w, emx, emn, nv);
   }
 }
 
@@ -472,6 +520,21 @@ k_reset_state(const EnvDev d, const uint8_t* __restrict__ mask, int32_t* __restr
     d.last_value[ia] = 0.0;
   }
   d.tick[e] = 0;
+  {
+    unsigned long long p0 = ~0ull, p1 = ~0ull;
+    for (int a = 0; a < A; ++a) {
+      const unsigned long long c = (unsigned long long)((start[a].y * G + start[a].x) & 0xffff);
+      const int sh = 16 * (a & 3);
+      if (a < 4)
+        p0 = (p0 & ~(0xffffull << sh)) | (c << sh);
+      else
+        p1 = (p1 & ~(0xffffull << sh)) | (c << sh);
+    }
+    uint2* rec = d.vrec + (size_t)e * d.rec_stride;
+    rec[0] = make_uint2(0u, 0u);
+    rec[1] = make_uint2((uint32_t)p0, (uint32_t)(p0 >> 32));
+    rec[2] = make_uint2((uint32_t)p1, (uint32_t)(p1 >> 32));
+  }
   double2* wp = reinterpret_cast<double2*>(d.welford + (size_t)e * 6);
   wp[0] = make_double2(0.0, 0.0);  // standardize.py:36-44
   wp[1] = make_double2(0.0, 1.0);
@@ -480,7 +543,7 @@ k_reset_state(const EnvDev d, const uint8_t* __restrict__ mask, int32_t* __restr
   reinterpret_cast<double2*>(d.est_mm)[e] = make_double2(0.0, 0.0);  // estimator.py:25-29
 }
 
-// visit (2 B) + head (2 B) + intensity (4 B) per cell; 16-byte stores, one CTA-row per env.
+// visit (2 B) + head (2 B) + slot (2 B) + intensity (4 B) per cell; 16-byte stores, one CTA per env.
 __global__ void __launch_bounds__(256)
 k_zero_maps(const EnvDev d, const uint8_t* __restrict__ mask) {
   const int e = blockIdx.x;
@@ -489,17 +552,20 @@ k_zero_maps(const EnvDev d, const uint8_t* __restrict__ mask) {
   const size_t b16 = (size_t)d.cells * 2, b32 = (size_t)d.cells * 4;
   unsigned char* v = reinterpret_cast<unsigned char*>(d.visit) + (size_t)e * b16;
   unsigned char* h = reinterpret_cast<unsigned char*>(d.head) + (size_t)e * b16;
+  unsigned char* sl = reinterpret_cast<unsigned char*>(d.slot) + (size_t)e * b16;
   unsigned char* f = reinterpret_cast<unsigned char*>(d.inten) + (size_t)e * b32;
   if ((d.cells & 7) == 0) {
     for (size_t i = threadIdx.x * 16; i < b16; i += blockDim.x * 16) {
       *reinterpret_cast<uint4*>(v + i) = z;
       *reinterpret_cast<uint4*>(h + i) = z;
+      *reinterpret_cast<uint4*>(sl + i) = z;
     }
     for (size_t i = threadIdx.x * 16; i < b32; i += blockDim.x * 16) *reinterpret_cast<uint4*>(f + i) = z;
   } else {
     for (int i = threadIdx.x; i < d.cells; i += blockDim.x) {
       d.visit[(size_t)e * d.cells + i] = 0;
       d.head[(size_t)e * d.cells + i] = 0;
+      d.slot[(size_t)e * d.cells + i] = 0;
       d.inten[(size_t)e * d.cells + i] = 0.f;
     }
   }
@@ -552,10 +618,8 @@ __device__ __forceinline__ void raster_chunk(float* __restrict__ o, int cells, c
   }
 }
 
-// kWithAgents = false is the "base" image used by the overlapped step: location channel all zero and
-// no read of agent_xy, so it may run concurrently with k_step; k_patch then fixes the <= A cells per env
-// that the step changed.  kUnroll chunks per thread are loaded before any is stored (bytes in flight).
-template <bool kLutInSmem, bool kWithAgents, int kUnroll>
+// kUnroll chunks per thread are loaded before any is stored (bytes in flight).
+template <bool kLutInSmem, int kUnroll>
 __global__ void __launch_bounds__(256)
 k_raster_vec(const EnvDev d, float* __restrict__ out, long long n_chunks) {
   extern __shared__ float s_lut[];
@@ -599,13 +663,11 @@ k_raster_vec(const EnvDev d, float* __restrict__ out, long long n_chunks) {
     for (int u = 0; u < kUnroll; ++u) {
       if (!ok[u]) continue;
       unsigned occ = 0u;
-      if (kWithAgents) {
-        const int2* agent = reinterpret_cast<const int2*>(d.agent_xy) + (size_t)ee[u] * A;
-        for (int a = 0; a < A; ++a) {
-          const int2 p = agent[a];
-          const unsigned r = (unsigned)(p.y * G + p.x - qq[u] * 8);
-          if (r < 8u) occ |= 1u << r;
-        }
+      const int2* agent = reinterpret_cast<const int2*>(d.agent_xy) + (size_t)ee[u] * A;
+      for (int a = 0; a < A; ++a) {
+        const int2 p = agent[a];
+        const unsigned r = (unsigned)(p.y * G + p.x - qq[u] * 8);
+        if (r < 8u) occ |= 1u << r;
       }
       raster_chunk(out + (size_t)ee[u] * 3 * d.cells + (size_t)qq[u] * 8, d.cells, vv[u], i0[u], i1[u], occ, lut);
     }
@@ -613,19 +675,42 @@ k_raster_vec(const EnvDev d, float* __restrict__ out, long long n_chunks) {
 }
 
 // --------------------------------------------------------------------------------------------
-// K3, resource-light form for the overlapped step: the same "base" image (location = 0, intensity,
-// visit table) moved by the bulk-copy (TMA) engine instead of the LSU.  One persistent CTA of 128
-// threads per SM-slot walks envs e = blockIdx.x, + gridDim.x, ... through a ring of kStages stages:
-//     bulk g2s   intensity (4*cells B) + visit counts (2*cells B)      -> stage, mbarrier expect_tx
-//     threads    visit u16 -> table value f32 (8 cells per thread-iteration, smem to smem)
-//     bulk s2g   zero tile -> channel 0, intensity stage -> channel 1, table values -> channel 2
-// Thread 0 issues every async operation; a stage is refilled only after the bulk stores that read it
-// have finished reading (cp.async.bulk.wait_group.read).  ~256 threads and ~40 registers per SM stream
-// the whole tensor, so k_step's CTAs co-reside and their latency hides under the stream.
+// K3, sparse form (default): a map of a 120-step episode has at most a few dozen non-zero cells, so the
+// rasteriser does not re-read the dense maps (6 KB/env).  It reads the env's compact record list kept
+// by k_step — header, agent cells and the first records in ONE bulk async copy (TMA engine, UBLKCP) —
+// composes the env's whole [3][G][G] tile in shared memory (zero, scatter records, mark agents) and
+// ships it with ONE 12 KB bulk store.  HBM traffic per env-step: 12,288 B written + rec_prefix*8 B read.
+// One CTA of 128 threads walks envs blockIdx.x, + gridDim.x, ... through a ring of kSpStages
+// (tile, record buffer) stages; thread 0 issues every async operation.
 __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
                "r"(smem_u32(src_smem)), "r"(bytes)
                : "memory");
+}
+// L2 cache policies: the observation tensor is written once and not re-read by us (evict first), the
+// record lists are re-read every step by k_step and the rasteriser (evict last).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_s2g_hint(void* dst_gmem, const void* src_smem, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
+               "r"(smem_u32(src_smem)), "r"(bytes), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                              uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -635,96 +720,87 @@ __device__ __forceinline__ void bulk_wait_read() {
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-constexpr int kTmaThreads = 128;
-__host__ __device__ inline size_t raster_tma_smem_bytes(int cells, int stages, int lut_entries) {
-  // [barriers 8*stages -> 128 B] [zero tile 4*cells] [stages x (inten 4*cells | visit 2*cells | table 4*cells)] [lut]
-  return 128 + (size_t)cells * 4 + (size_t)stages * cells * 10 + (size_t)lut_entries * 4;
+constexpr int kSpWarps = 8;      // warps per CTA, each an independent pipeline
+constexpr int kSpThreads = kSpWarps * 32;
+constexpr int kSpStages = 2;     // (tile, record buffer) stages per warp
+__host__ __device__ inline size_t raster_sparse_smem_bytes(int cells, int prefix, int lut_entries) {
+  // [mbarriers, 128 B] [kSpWarps*kSpStages tiles of 12*cells B] [as many record buffers of 8*prefix B] [table]
+  return 128 + (size_t)kSpWarps * kSpStages * ((size_t)cells * 12 + (size_t)prefix * 8) + (size_t)lut_entries * 4;
 }
 
+// Every WARP is an autonomous pipeline over its own envs (global warp id, + total warps, ...): no CTA
+// barrier in the loop.  Lane 0 issues the bulk copies and owns their completion (bulk groups and
+// mbarrier arrivals are per thread); the lanes zero the tile, scatter the records and mark the agents.
+// While the bulk store of one tile drains, the warp composes the other.
 template <bool kLutInSmem>
-__global__ void __launch_bounds__(kTmaThreads)
-k_raster_base_tma(const EnvDev d, float* __restrict__ out, int stages) {
+__global__ void __launch_bounds__(kSpThreads, 1)
+k_raster_sparse(const EnvDev d, float* __restrict__ out, int hints) {
   extern __shared__ __align__(128) unsigned char sm[];
-  const int cells = d.cells;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sm);
-  float* zero = reinterpret_cast<float*>(sm + 128);
-  unsigned char* ring = sm + 128 + (size_t)cells * 4;
-  const size_t stage_bytes = (size_t)cells * 10;
-  float* s_lut = reinterpret_cast<float*>(ring + (size_t)stages * stage_bytes);
-  const int tid = threadIdx.x;
-  const uint32_t in_bytes = (uint32_t)cells * 6u, f_bytes = (uint32_t)cells * 4u;
+  const int cells = d.cells, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint32_t tile_bytes = (uint32_t)cells * 12u, pre_bytes = (uint32_t)d.rec_prefix * 8u;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm) + w * kSpStages;
+  unsigned char* tiles = sm + 128 + (size_t)w * kSpStages * tile_bytes;
+  unsigned char* recs = sm + 128 + (size_t)kSpWarps * kSpStages * tile_bytes + (size_t)w * kSpStages * pre_bytes;
+  float* s_lut = reinterpret_cast<float*>(sm + 128 + (size_t)kSpWarps * kSpStages * (tile_bytes + pre_bytes));
 
-  for (int i = tid; i < cells; i += kTmaThreads) zero[i] = 0.0f;
   if (kLutInSmem)
-    for (int i = tid; i <= d.cap; i += kTmaThreads) s_lut[i] = d.lut[i];
-  if (tid == 0)
-    for (int s = 0; s < stages; ++s) mbar_init(full + s, 1u);
-  fence_proxy_async();  // zero tile (generic writes) will be read by bulk stores
-  __syncthreads();
+    for (int i = tid; i <= d.cap; i += kSpThreads) s_lut[i] = d.lut[i];
+  if (lane == 0)
+    for (int s = 0; s < kSpStages; ++s) mbar_init(full + s, 1u);
+  __syncthreads();  // the only CTA-wide barrier: table staged, barriers initialised
   const float* lut = kLutInSmem ? s_lut : d.lut;
 
-  const int n_mine = (d.E - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // envs of this CTA
-  auto issue_load = [&](int k) {  // thread 0: env k of this CTA into stage k % stages
-    const int s = k % stages;
-    const size_t e = (size_t)blockIdx.x + (size_t)k * gridDim.x;
-    unsigned char* st = ring + (size_t)s * stage_bytes;
-    mbar_arrive_expect_tx(full + s, in_bytes);
-    bulk_g2s(st, d.inten + e * cells, f_bytes, full + s);
-    bulk_g2s(st + f_bytes, d.visit + e * cells, (uint32_t)cells * 2u, full + s);
+  const uint64_t pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
+  const long long n_warps = (long long)gridDim.x * kSpWarps;
+  const long long gw = (long long)blockIdx.x * kSpWarps + w;
+  const int n_mine = gw < d.E ? (int)((d.E - gw + n_warps - 1) / n_warps) : 0;  // envs of this warp
+  auto issue_load = [&](int k) {  // lane 0: record prefix of this warp's env k into stage k % kSpStages
+    const int s = k % kSpStages;
+    const size_t e = (size_t)(gw + (long long)k * n_warps);
+    mbar_arrive_expect_tx(full + s, pre_bytes);
+    if (hints & 2)
+      bulk_g2s_hint(recs + (size_t)s * pre_bytes, d.vrec + e * d.rec_stride, pre_bytes, full + s, pol_last);
+    else
+      bulk_g2s(recs + (size_t)s * pre_bytes, d.vrec + e * d.rec_stride, pre_bytes, full + s);
   };
-  if (tid == 0)
-    for (int k = 0; k < stages - 1 && k < n_mine; ++k) issue_load(k);
+  if (lane == 0)
+    for (int k = 0; k < kSpStages && k < n_mine; ++k) issue_load(k);
 
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int k = 0; k < n_mine; ++k) {
-    const int s = k % stages;
-    unsigned char* st = ring + (size_t)s * stage_bytes;
-    const uint4* visit = reinterpret_cast<const uint4*>(st + f_bytes);
-    float4* table = reinterpret_cast<float4*>(st + f_bytes + (size_t)cells * 2);
-    mbar_wait(full + s, (uint32_t)((k / stages) & 1));
-    for (int i = tid; i < (cells >> 3); i += kTmaThreads) {
-      const uint4 vv = visit[i];
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-      if ((vv.x | vv.y | vv.z | vv.w) != 0u) {
-        a = make_float4(lut[vv.x & 0xffffu], lut[vv.x >> 16], lut[vv.y & 0xffffu], lut[vv.y >> 16]);
-        b = make_float4(lut[vv.z & 0xffffu], lut[vv.z >> 16], lut[vv.w & 0xffffu], lut[vv.w >> 16]);
-      }
-      table[2 * i] = a;
-      table[2 * i + 1] = b;
+    const int s = k % kSpStages;
+    const size_t e = (size_t)(gw + (long long)k * n_warps);
+    float* tile = reinterpret_cast<float*>(tiles + (size_t)s * tile_bytes);
+    const uint2* rec = reinterpret_cast<const uint2*>(recs + (size_t)s * pre_bytes);
+    // the bulk store that last read this tile (kSpStages envs ago) must have finished reading it
+    if (lane == 0 && k >= kSpStages) bulk_wait_read<kSpStages - 1>();
+    __syncwarp();
+    for (int i = lane; i < (cells * 3) >> 2; i += 32) reinterpret_cast<float4*>(tile)[i] = z4;
+    mbar_wait(full + s, (uint32_t)((k / kSpStages) & 1));  // record prefix has landed
+    __syncwarp();  // zeroing by all lanes is ordered before any lane's scatter
+    const int nv = (int)rec[0].x;
+    for (int i = lane; i < nv; i += 32) {
+      const uint2 r = (3 + i < d.rec_prefix) ? rec[3 + i] : d.vrec[e * d.rec_stride + 3 + i];
+      const int cell = (int)(r.x & 0xffffu);
+      tile[cells + cell] = __uint_as_float(r.y);
+      tile[2 * cells + cell] = lut[r.x >> 16];
     }
-    fence_proxy_async();  // table values (generic writes) -> visible to the bulk store
-    __syncthreads();
-    if (tid == 0) {
-      const size_t e = (size_t)blockIdx.x + (size_t)k * gridDim.x;
-      float* o = out + e * 3 * cells;
-      bulk_s2g(o, zero, f_bytes);
-      bulk_s2g(o + cells, st, f_bytes);
-      bulk_s2g(o + 2 * (size_t)cells, table, f_bytes);
+    if (lane < RT_MAX_AGENTS) {
+      const uint32_t c = reinterpret_cast<const uint16_t*>(rec + 1)[lane];
+      if (c != 0xffffu) tile[c] = 1.0f;
+    }
+    fence_proxy_async();  // generic-proxy writes of the tile -> visible to the bulk store
+    __syncwarp();         // also: every lane is done reading this stage's record buffer
+    if (lane == 0) {
+      if (hints & 1)
+        bulk_s2g_hint(out + e * 3 * (size_t)cells, tile, tile_bytes, pol_first);
+      else
+        bulk_s2g(out + e * 3 * (size_t)cells, tile, tile_bytes);
       bulk_commit();
-      // the stage that env k + stages - 1 will use is the one env k - 1 used: its stores (the group
-      // before this one) must have finished reading shared memory before it is overwritten
-      if (k + stages - 1 < n_mine) {
-        bulk_wait_read<1>();
-        issue_load(k + stages - 1);
-      }
+      if (k + kSpStages < n_mine) issue_load(k + kSpStages);
     }
   }
-  if (tid == 0) bulk_wait_all();
-}
-
-// After k_step and the base image: one thread per (env, agent) rewrites the agent's cell in all three
-// channels from the final map state (two agents on one cell write the same values).
-__global__ void __launch_bounds__(256)
-k_patch(const EnvDev d, float* __restrict__ out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)d.E * d.A) return;
-  const int e = (int)(i / d.A);
-  const int2 p = reinterpret_cast<const int2*>(d.agent_xy)[i];
-  const int cell = p.y * d.G + p.x;
-  const size_t m = (size_t)e * d.cells + cell;
-  float* o = out + (size_t)e * 3 * d.cells + cell;
-  o[0] = 1.0f;
-  o[d.cells] = d.inten[m];
-  o[2 * (size_t)d.cells] = d.lut[d.visit[m]];
+  if (lane == 0) bulk_wait_all();
 }
 
 // Generic path for any grid side (the reference default size=10 has 100 cells): one cell per thread.

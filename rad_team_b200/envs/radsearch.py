@@ -78,6 +78,8 @@ _BUF_SPEC = {
     "VISIT_LUT": ("float32", lambda E, A, c, cap: (cap + 1,)),
     "EP_RETURN": ("int32", lambda E, A, c, cap: (E, A)),
     "EP_DONE": ("uint8", lambda E, A, c, cap: (E, A)),
+    "SLOT": ("uint16", lambda E, A, c, cap: (E, c)),
+    "VREC": ("int32", lambda E, A, c, cap: (E, (3 + min(cap, c) + 1) & ~1, 2)),
 }
 _ITEMSIZE = {"int32": 4, "float64": 8, "float32": 4, "uint16": 2, "uint8": 1}
 
