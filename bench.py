@@ -20,7 +20,7 @@ Workloads (BASELINE.json configs):
 One JSON line on stdout (rank 0).  `value`: inputs resident in HBM, CUDA-event time, max over ranks.
 `e2e`: the same loop through the host-buffer C-ABI entry points (rt_env_step_host): pinned actions copied
 up and obs_xy / reward / done copied back EVERY step inside the timed region, wall clock, max over ranks.
-`roofline`: the rasteriser (dominant kernel) timed live with CUDA events around its own launch.
+`roofline`: the rasteriser (dominant kernel) timed live with CUDA events around its own launch inside the step.
 `cpu_baseline`: the CPU oracle (C port of the reference algorithm) on this box's host cores, bounded sample.
 """
 from __future__ import annotations
@@ -125,7 +125,8 @@ def measured_peak_gbs():
 
 
 def ncu_traffic_per_launch(n_envs):
-    """dram bytes per raster launch from the committed ncu capture, scaled per env (profiles/)."""
+    """dram bytes (read + write) per rasteriser launch from the committed ncu --set full capture
+    (profiles/raster_traffic.json), scaled per env."""
     p = REPO / "profiles" / "raster_traffic.json"
     if p.exists():
         try:
@@ -343,23 +344,27 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = total_agents * K2 / e2e_s
 
     peak, peak_src = measured_peak_gbs()
-    raster_bytes = E * (3 * GRID * GRID * 4 + GRID * GRID * (2 + 4))  # 18,432 B / env-step
-    step_bytes = E * A * (150 + 104)                                   # K1+K2 150, K4a 104 B / agent-step
-    fused = os.environ.get("RT_B200_OVERLAP", "1") != "0"
-    # the rasteriser is the dominant kernel either way; in the overlapped step it runs concurrently
-    # with k_step, so the whole step's launch group is what the events bracket
-    dom_bytes, dom_ms, dom_name = ((raster_bytes + step_bytes, fused_ms,
-                                    "step group: k_raster_vec(base) || k_step, then k_patch")
-                                   if fused else (raster_bytes, raster_ms, "k_raster_vec (K3)"))
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    # Algorithmic bytes per launch.  Default rasteriser k_raster_sparse: 12,288 B stored +
+    # 1,024 B loaded (record prefix) per env-step.  SURVEY §8d's K3 figure, 18,432 B/env-step, assumes the dense
+    # maps are re-read every step (that is k_raster_vec, RT_B200_RASTER=dense); it is reported as
+    # `survey_equiv_*` so the two designs can be compared on one scale.
+    dense = os.environ.get("RT_B200_RASTER", "") == "dense"
+    survey_bytes = E * (3 * GRID * GRID * 4 + GRID * GRID * (2 + 4))
+    raster_bytes = survey_bytes if dense else E * (3 * GRID * GRID * 4 + 128 * 8)
+    rname = "k_raster_vec (K3, dense maps)" if dense else "k_raster_sparse (K3, visited-cell records + TMA bulk tiles)"
+    achieved = raster_bytes / (raster_ms * 1e-3) / 1e9
+    step_bytes = E * A * (150 + 104)  # K1+K2 150, K4a 104 B / agent-step
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic_per_launch(E), "kernel": dom_name, "ms_per_launch": dom_ms,
-                "algorithmic_bytes_per_launch": dom_bytes, "peak_source": peak_src,
-                "regime": "HBM (per-launch footprint %.0f MB >> 126 MB L2)" % (dom_bytes / 1e6)
-                if dom_bytes > 4 * 126e6 else "L2-resident footprint (%.0f MB)" % (dom_bytes / 1e6),
-                "raster_alone": {"kernel": "k_raster_vec (K3)", "ms_per_launch": raster_ms,
-                                 "achieved": raster_bytes / (raster_ms * 1e-3) / 1e9,
-                                 "frac": raster_bytes / (raster_ms * 1e-3) / 1e9 / peak}}
+                "traffic": ncu_traffic_per_launch(E), "kernel": rname, "ms_per_launch": raster_ms,
+                "algorithmic_bytes_per_launch": raster_bytes, "peak_source": peak_src,
+                "timing": "CUDA events around the rasteriser's own launch, issued right after k_step inside the step loop",
+                "regime": "HBM (per-launch footprint %.0f MB >> 126 MB L2)" % (raster_bytes / 1e6)
+                if raster_bytes > 4 * 126e6 else "L2-resident footprint (%.0f MB)" % (raster_bytes / 1e6),
+                "survey_equiv_achieved": survey_bytes / (raster_ms * 1e-3) / 1e9,
+                "survey_equiv_frac": survey_bytes / (raster_ms * 1e-3) / 1e9 / peak,
+                "whole_step": {"ms": fused_ms, "algorithmic_bytes": raster_bytes + step_bytes,
+                               "achieved": (raster_bytes + step_bytes) / (fused_ms * 1e-3) / 1e9,
+                               "frac": (raster_bytes + step_bytes) / (fused_ms * 1e-3) / 1e9 / peak}}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -376,12 +381,13 @@ def run_ours(args, rank, world, local_rank):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["name"], "envs_per_gpu": E, "agents": A, "grid": GRID, "episode_steps": T_EPISODE,
-                       "l2": "inputs larger than L2: each step streams %.0f MB per GPU" % (raster_bytes / 1e6),
+                       "l2": "inputs larger than L2: each step streams %.0f MB per GPU (obs tensor %.0f MB alone)"
+                             % (raster_bytes / 1e6, E * 3 * GRID * GRID * 4 / 1e6),
                        "rollout_close": "every 120 steps: batch Welford moments + episode stats"
                                         + (" + NCCL all-gather/merge" if world > 1 else "") + " + reset, inside the timed region",
                        "arithmetic": "fp64 physics/statistics, fp32 geometry and maps, int32 indices/counts"},
             "roofline": roofline,
-            "kernels": {"step_group_ms": fused_ms, "k_step_ms": kstep_ms, "k_raster_vec_ms": raster_ms},
+            "kernels": {"step_ms": fused_ms, "k_step_ms": kstep_ms, "raster_ms": raster_ms},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "agent-env-steps/s", "h2d_bytes_per_step": E * A * 4,
                     "d2h_bytes_per_step": E * A * 13, "steps": K2,

@@ -232,7 +232,7 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
   size_t off[RT_BUF__COUNT];
   for (int i = 0; i < RT_BUF__COUNT; ++i) off[i] = cv.take(sz[i]);
   const size_t o_act = cv.take(E * A * 4), o_xy = cv.take(E * A * 8), o_rw = cv.take(E * A * 4),
-               o_dn = cv.take(E * A), o_mask = cv.take(E), o_for = cv.take(4);
+               o_dn = cv.take(E * A), o_mask = cv.take(E), o_for = cv.take(8);
   h->slab_bytes = cv.off;
   if (cudaMalloc(&h->slab, h->slab_bytes) != cudaSuccess) {
     rt_note_cuda_error(cudaGetLastError(), "cudaMalloc(slab)");
@@ -300,6 +300,7 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
   d.rec_stride = rec_stride;
   d.rec_prefix = rec_stride < 128 ? rec_stride : 128;  // 1 KB per env covers 125 visited cells; the rest is read directly
   d.rollout = nullptr;
+  d.step_flags = h->d_flag_or + 1;
   d.inj = nullptr;
   d.inj_k = 0;
 
@@ -452,16 +453,15 @@ int rt_env_step_host(rt_env* h, const int32_t* actions_host, int32_t* obs_xy_hos
   unsigned char* p_xy = h->pinned + n * 4;
   unsigned char* p_rw = h->pinned + n * 12;
   unsigned char* p_dn = h->pinned + n * 16;
-  // invalid actions are also caught on the device, but the reference raises before any
-  // state change (simple_gridworld.py:138), so check on the host first
-  for (size_t i = 0; i < n; ++i)
-    if (actions_host[i] < 1 || actions_host[i] > 4) return RT_ERR_BAD_ACTION;
+  // Invalid actions are caught on the device: the env's step is voided (the reference raises before any
+  // state change, simple_gridworld.py:138) and a flag word travels back with the results.
   const void* a_src = actions_host;
   if (!is_pinned_or_device(actions_host)) {
     std::memcpy(p_act, actions_host, n * 4);
     a_src = p_act;
   }
   RT_CUDA(cudaMemcpyAsync(h->d_actions, a_src, n * 4, cudaMemcpyHostToDevice, st));
+  RT_CUDA(cudaMemsetAsync(h->dev.step_flags, 0, 4, st));
   // k_step, then the small results travel back on the auxiliary stream WHILE the rasteriser streams
   int rc = launch_step(h, h->d_actions, h->d_obs_xy, nullptr, h->d_reward, h->d_done, st);
   if (rc != RT_OK) return rc;
@@ -472,6 +472,8 @@ int rt_env_step_host(rt_env* h, const int32_t* actions_host, int32_t* obs_xy_hos
   RT_CUDA(cudaMemcpyAsync(dx ? (void*)obs_xy_host : (void*)p_xy, h->d_obs_xy, n * 8, cudaMemcpyDeviceToHost, h->aux));
   RT_CUDA(cudaMemcpyAsync(dr ? (void*)reward_host : (void*)p_rw, h->d_reward, n * 4, cudaMemcpyDeviceToHost, h->aux));
   RT_CUDA(cudaMemcpyAsync(dd ? (void*)done_host : (void*)p_dn, h->d_done, n, cudaMemcpyDeviceToHost, h->aux));
+  int32_t* p_fl = reinterpret_cast<int32_t*>(h->pinned + h->pinned_bytes - 16);
+  RT_CUDA(cudaMemcpyAsync(p_fl, h->dev.step_flags, 4, cudaMemcpyDeviceToHost, h->aux));
   if (obs_maps_dev) {
     rc = launch_raster(h, obs_maps_dev, st);
     if (rc != RT_OK) return rc;
@@ -481,6 +483,7 @@ int rt_env_step_host(rt_env* h, const int32_t* actions_host, int32_t* obs_xy_hos
   if (!dx) std::memcpy(obs_xy_host, p_xy, n * 8);
   if (!dr) std::memcpy(reward_host, p_rw, n * 4);
   if (!dd) std::memcpy(done_host, p_dn, n);
+  if (*p_fl & RT_FLAG_BAD_ACTION) return RT_ERR_BAD_ACTION;
   return RT_OK;
 }
 

@@ -57,6 +57,7 @@ struct EnvDev {
   int32_t* ep_return;  // [E][A]
   uint8_t* ep_done;    // [E][A]
   float* rollout;      // [T][E][A] readings sink, or nullptr
+  int32_t* step_flags; // one word: OR of the RT_FLAG_* that voided an env's step in the CURRENT launch
   const double* inj;
   int inj_k;
 };
@@ -414,10 +415,12 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
 
   // ---- K4a: the env's sequential statistics -------------------------------------------------------
   if (valid && a == 0) {
-    if (skip)
+    if (skip) {
       atomicOr(&d.flags[e], skip);
-    else
+      atomicOr(d.step_flags, skip);
+    } else {
       stats_chain(d, s, e, le, tick, w, emx, emn, nv);
+    }
   }
 }
 
