@@ -351,7 +351,7 @@ def run_ours(args, rank, world, local_rank):
     dense = os.environ.get("RT_B200_RASTER", "") == "dense"
     survey_bytes = E * (3 * GRID * GRID * 4 + GRID * GRID * (2 + 4))
     raster_bytes = survey_bytes if dense else E * (3 * GRID * GRID * 4 + 128 * 8)
-    rname = "k_raster_vec (K3, dense maps)" if dense else "k_raster_sparse (K3, visited-cell records + TMA bulk tiles)"
+    rname = "k_raster_vec (K3, dense maps)" if dense else "k_raster_sparse_lsu (K3, visited-cell records -> smem tile -> coalesced 16 B stores)"
     achieved = raster_bytes / (raster_ms * 1e-3) / 1e9
     step_bytes = E * A * (150 + 104)  # K1+K2 150, K4a 104 B / agent-step
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

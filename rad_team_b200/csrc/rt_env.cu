@@ -38,7 +38,8 @@ struct rt_env {
   cudaEvent_t ev_fork = nullptr;
   int raster_ctas = 32, raster_unroll = 2;  // dense rasteriser: CTAs per SM (grid cap), chunks in flight per thread
   bool sparse = true;                       // RT_B200_RASTER=dense selects the dense (LSU) rasteriser
-  int sparse_ctas = 1;                      // sparse rasteriser: persistent CTAs (8 warp pipelines each) per SM
+  int sparse_ctas = 4;                      // k_raster_sparse_lsu: CTAs (8 warp pipelines each) per SM in the grid (2 resident)
+  bool sparse_lsu = true;                   // RT_B200_RASTER=sparse_tma selects the bulk-store variant
   int sparse_hints = 3;                     // bit 0: evict-first bulk stores, bit 1: evict-last record loads
 };
 
@@ -129,9 +130,17 @@ void launch_raster_vec(rt_env* h, float* obs_maps, cudaStream_t st) {
 
 int launch_raster(rt_env* h, float* obs_maps, cudaStream_t st) {
   const EnvDev& d = h->dev;
-  if (h->sparse) {
-    const size_t smb = raster_sparse_smem_bytes(d.cells, d.rec_prefix, h->lut_in_smem ? d.cap + 1 : 0);
+  if (h->sparse && h->sparse_lsu) {
+    const size_t smb = raster_sl_smem_bytes(d.cells, h->lut_in_smem ? d.cap + 1 : 0);
     long long nb = (long long)h->n_sm * h->sparse_ctas;
+    if (nb * kSlWarps > d.E) nb = (d.E + kSlWarps - 1) / kSlWarps;
+    if (h->lut_in_smem)
+      k_raster_sparse_lsu<true><<<(unsigned)nb, kSlThreads, smb, st>>>(d, obs_maps);
+    else
+      k_raster_sparse_lsu<false><<<(unsigned)nb, kSlThreads, smb, st>>>(d, obs_maps);
+  } else if (h->sparse) {
+    const size_t smb = raster_sparse_smem_bytes(d.cells, d.rec_prefix, h->lut_in_smem ? d.cap + 1 : 0);
+    long long nb = (long long)h->n_sm;  // 16 tiles fill an SM's shared memory: one persistent CTA each
     if (nb * kSpWarps > d.E) nb = (d.E + kSpWarps - 1) / kSpWarps;
     if (h->lut_in_smem)
       k_raster_sparse<true><<<(unsigned)nb, kSpThreads, smb, st>>>(d, obs_maps, h->sparse_hints);
@@ -346,7 +355,10 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
   if (const char* ev = std::getenv("RT_B200_RASTER_UNROLL")) h->raster_unroll = std::max(1, std::atoi(ev));
   if (const char* ev = std::getenv("RT_B200_SPARSE_CTAS")) h->sparse_ctas = std::max(1, std::atoi(ev));
   if (const char* ev = std::getenv("RT_B200_SPARSE_HINTS")) h->sparse_hints = std::atoi(ev);
-  if (const char* ev = std::getenv("RT_B200_RASTER")) h->sparse = std::strcmp(ev, "dense") != 0;
+  if (const char* ev = std::getenv("RT_B200_RASTER")) {
+    h->sparse = std::strcmp(ev, "dense") != 0;
+    h->sparse_lsu = std::strcmp(ev, "sparse_tma") != 0;
+  }
   {
     // the sparse rasteriser composes whole [3][G][G] tiles in shared memory: needs cells % 8 == 0, cell
     // indices that fit 16 bits and kSpStages tiles within the opt-in shared memory; otherwise dense
@@ -357,6 +369,11 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
       RT_CUDA_OR(cudaFuncSetAttribute(k_raster_sparse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb),
                  { rt_env_destroy(h); });
       RT_CUDA_OR(cudaFuncSetAttribute(k_raster_sparse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb),
+                 { rt_env_destroy(h); });
+      const size_t sml = raster_sl_smem_bytes((int)cells, h->lut_in_smem ? (int)cap + 1 : 0);
+      RT_CUDA_OR(cudaFuncSetAttribute(k_raster_sparse_lsu<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sml),
+                 { rt_env_destroy(h); });
+      RT_CUDA_OR(cudaFuncSetAttribute(k_raster_sparse_lsu<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sml),
                  { rt_env_destroy(h); });
     }
   }

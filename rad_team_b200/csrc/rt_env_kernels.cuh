@@ -766,7 +766,8 @@ k_raster_sparse(const EnvDev d, float* __restrict__ out, int hints) {
     else
       bulk_g2s(recs + (size_t)s * pre_bytes, d.vrec + e * d.rec_stride, pre_bytes, full + s);
   };
-  if (lane == 0)
+  const bool x_nocompose = hints & 4, x_noload = hints & 8;  // experiment knobs (profiles/r01p): not for use
+  if (lane == 0 && !x_noload)
     for (int k = 0; k < kSpStages && k < n_mine; ++k) issue_load(k);
 
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -778,17 +779,18 @@ k_raster_sparse(const EnvDev d, float* __restrict__ out, int hints) {
     // the bulk store that last read this tile (kSpStages envs ago) must have finished reading it
     if (lane == 0 && k >= kSpStages) bulk_wait_read<kSpStages - 1>();
     __syncwarp();
-    for (int i = lane; i < (cells * 3) >> 2; i += 32) reinterpret_cast<float4*>(tile)[i] = z4;
-    mbar_wait(full + s, (uint32_t)((k / kSpStages) & 1));  // record prefix has landed
+    if (!x_nocompose)
+      for (int i = lane; i < (cells * 3) >> 2; i += 32) reinterpret_cast<float4*>(tile)[i] = z4;
+    if (!x_noload) mbar_wait(full + s, (uint32_t)((k / kSpStages) & 1));  // record prefix has landed
     __syncwarp();  // zeroing by all lanes is ordered before any lane's scatter
-    const int nv = (int)rec[0].x;
+    const int nv = (x_nocompose || x_noload) ? 0 : (int)rec[0].x;
     for (int i = lane; i < nv; i += 32) {
       const uint2 r = (3 + i < d.rec_prefix) ? rec[3 + i] : d.vrec[e * d.rec_stride + 3 + i];
       const int cell = (int)(r.x & 0xffffu);
       tile[cells + cell] = __uint_as_float(r.y);
       tile[2 * cells + cell] = lut[r.x >> 16];
     }
-    if (lane < RT_MAX_AGENTS) {
+    if (lane < RT_MAX_AGENTS && !x_nocompose && !x_noload) {
       const uint32_t c = reinterpret_cast<const uint16_t*>(rec + 1)[lane];
       if (c != 0xffffu) tile[c] = 1.0f;
     }
@@ -800,10 +802,104 @@ k_raster_sparse(const EnvDev d, float* __restrict__ out, int hints) {
       else
         bulk_s2g(out + e * 3 * (size_t)cells, tile, tile_bytes);
       bulk_commit();
-      if (k + kSpStages < n_mine) issue_load(k + kSpStages);
+      if (k + kSpStages < n_mine && !x_noload) issue_load(k + kSpStages);
     }
   }
   if (lane == 0) bulk_wait_all();
+}
+
+// K3, sparse form with LSU stores.  Measured on B200 (profiles/r01p): a pure stream of 12 KB bulk (TMA)
+// stores tops out at 6.2 TB/s and interleaved record reads cost it disproportionately, while plain
+// coalesced stores reach the 7.4 TB/s of a fill.  So here every warp owns ONE tile in shared memory
+// (zeroed once), and per env: the first 128 record slots arrive in registers (4 x 8 B per lane, loaded
+// one env ahead), the lanes scatter them into the tile, the warp streams the tile out with 24 coalesced
+// 16-byte stores per lane, and the scattered cells are cleared again.  No barriers beyond __syncwarp.
+constexpr int kSlWarps = 8;
+constexpr int kSlThreads = kSlWarps * 32;
+__host__ __device__ inline size_t raster_sl_smem_bytes(int cells, int lut_entries) {
+  return (size_t)kSlWarps * cells * 12 + (size_t)lut_entries * 4;
+}
+
+template <bool kLutInSmem>
+__global__ void __launch_bounds__(kSlThreads)
+k_raster_sparse_lsu(const EnvDev d, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  const int cells = d.cells, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  float* tile = reinterpret_cast<float*>(sm + (size_t)w * cells * 12);
+  float* s_lut = reinterpret_cast<float*>(sm + (size_t)kSlWarps * cells * 12);
+  if (kLutInSmem)
+    for (int i = tid; i <= d.cap; i += kSlThreads) s_lut[i] = d.lut[i];
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int n4 = (cells * 3) >> 2;  // float4 per tile
+  for (int i = lane; i < n4; i += 32) reinterpret_cast<float4*>(tile)[i] = z4;
+  __syncthreads();  // table staged (the only CTA-wide barrier)
+  const float* lut = kLutInSmem ? s_lut : d.lut;
+
+  const long long n_warps = (long long)gridDim.x * kSlWarps;
+  const long long gw = (long long)blockIdx.x * kSlWarps + w;
+  auto load4 = [&](long long e, uint2 (&r)[4]) {  // slots lane, lane+32, lane+64, lane+96 of env e
+    const uint2* p = d.vrec + (size_t)e * d.rec_stride;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int j = lane + 32 * m;
+      r[m] = j < d.rec_stride ? p[j] : make_uint2(0u, 0u);
+    }
+  };
+  uint2 nxt[4] = {make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u)};
+  if (gw < d.E) load4(gw, nxt);
+  for (long long e = gw; e < d.E; e += n_warps) {
+    uint2 cur[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) cur[m] = nxt[m];
+    if (e + n_warps < d.E) load4(e + n_warps, nxt);  // next env's records fly while this one is composed
+    const int nv = (int)__shfl_sync(0xffffffffu, cur[0].x, 0);
+    // agent cells: slots 1 and 2 (lanes 1, 2) hold 8 x uint16
+    const uint32_t w1x = __shfl_sync(0xffffffffu, cur[0].x, 1), w1y = __shfl_sync(0xffffffffu, cur[0].y, 1);
+    const uint32_t w2x = __shfl_sync(0xffffffffu, cur[0].x, 2), w2y = __shfl_sync(0xffffffffu, cur[0].y, 2);
+    int acell = 0xffff;
+    if (lane < RT_MAX_AGENTS) {
+      const uint32_t word = lane < 2 ? w1x : (lane < 4 ? w1y : (lane < 6 ? w2x : w2y));
+      acell = (int)((lane & 1) ? (word >> 16) : (word & 0xffffu));
+      if (acell != 0xffff) tile[acell] = 1.0f;
+    }
+    // records: slot j = lane + 32 m holds record j - 3 (valid when 3 <= j < 3 + nv)
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int j = lane + 32 * m;
+      if (j >= 3 && j - 3 < nv) {
+        const int cell = (int)(cur[m].x & 0xffffu);
+        tile[cells + cell] = __uint_as_float(cur[m].y);
+        tile[2 * cells + cell] = lut[cur[m].x >> 16];
+      }
+    }
+    for (int j = 128 + lane; j - 3 < nv; j += 32) {  // rare: more than 125 visited cells
+      const uint2 r = d.vrec[(size_t)e * d.rec_stride + j];
+      const int cell = (int)(r.x & 0xffffu);
+      tile[cells + cell] = __uint_as_float(r.y);
+      tile[2 * cells + cell] = lut[r.x >> 16];
+    }
+    __syncwarp();
+    float* o = out + (size_t)e * 3 * cells;
+    for (int i = lane; i < n4; i += 32) st_stream_f4(o + 4 * i, reinterpret_cast<const float4*>(tile)[i]);
+    __syncwarp();
+    // clear exactly what was set
+    if (acell != 0xffff) tile[acell] = 0.0f;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int j = lane + 32 * m;
+      if (j >= 3 && j - 3 < nv) {
+        const int cell = (int)(cur[m].x & 0xffffu);
+        tile[cells + cell] = 0.0f;
+        tile[2 * cells + cell] = 0.0f;
+      }
+    }
+    for (int j = 128 + lane; j - 3 < nv; j += 32) {
+      const int cell = (int)(d.vrec[(size_t)e * d.rec_stride + j].x & 0xffffu);
+      tile[cells + cell] = 0.0f;
+      tile[2 * cells + cell] = 0.0f;
+    }
+    __syncwarp();
+  }
 }
 
 // Generic path for any grid side (the reference default size=10 has 100 cells): one cell per thread.

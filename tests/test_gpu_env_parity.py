@@ -275,9 +275,10 @@ def test_sharding_invariance_global_env_ids():
     dict(n_envs=9, n_agents=1, grid=16, max_steps=20, seed=18),
 ])
 def test_sparse_and_dense_rasterisers_agree(monkeypatch, kw):
-    """Default: k_raster_sparse composes tiles from the visited-cell records (TMA bulk copies).
-    RT_B200_RASTER=dense streams the dense maps (k_raster_vec).  step() and step(rasterize=False) +
-    rasterize() must all give identical tensors, and identical to the oracle."""
+    """Default: k_raster_sparse_lsu composes tiles from the visited-cell records and streams them out;
+    RT_B200_RASTER=sparse_tma does the same with bulk (TMA) copies; RT_B200_RASTER=dense streams the dense
+    maps (k_raster_vec).  step() and step(rasterize=False) + rasterize() must all give identical tensors,
+    and identical to the oracle."""
     import torch
     from oracle import oracle as O
     from rad_team_b200.envs import BatchedRadSearchEnv
@@ -291,10 +292,13 @@ def test_sparse_and_dense_rasterisers_agree(monkeypatch, kw):
     monkeypatch.delenv("RT_B200_RASTER"); monkeypatch.delenv("RT_B200_EPB"); monkeypatch.delenv("RT_B200_RASTER_UNROLL")
     monkeypatch.setenv("RT_B200_SPARSE_CTAS", "1")
     split = BatchedRadSearchEnv(**full)
+    monkeypatch.setenv("RT_B200_RASTER", "sparse_tma")
+    tma = BatchedRadSearchEnv(**full)
+    monkeypatch.delenv("RT_B200_RASTER")
     orc = O.OracleEnv(**full)
     E, A, T = full["n_envs"], full["n_agents"], full["max_steps"]
     rng = np.random.default_rng(kw["seed"])
-    for env in (sparse, dense, split):
+    for env in (sparse, dense, split, tma):
         env.reset()
     _, m_o = orc.reset()
     assert np.array_equal(sparse.obs_maps.cpu().numpy(), m_o) and torch.equal(sparse.obs_maps, dense.obs_maps)
@@ -303,11 +307,12 @@ def test_sparse_and_dense_rasterisers_agree(monkeypatch, kw):
         if t % 3 == 0:  # drive agents along long straight paths so that many distinct cells get visited
             a_np[:] = 1 + (t // 30) % 4
         act = torch.as_tensor(a_np, device=sparse.device)
-        sparse.step(act); dense.step(act)
+        sparse.step(act); dense.step(act); tma.step(act)
         split.step(act, rasterize=False); split.rasterize()
         _, m_o, _, _ = orc.step(a_np)
         assert torch.equal(sparse.obs_maps, dense.obs_maps), t
         assert torch.equal(sparse.obs_maps, split.obs_maps), t
+        assert torch.equal(sparse.obs_maps, tma.obs_maps), t
         assert np.array_equal(sparse.obs_maps.cpu().numpy(), m_o), t
     for k in ("VISIT", "INTENSITY", "WELFORD", "LOG", "HEAD", "SLOT", "VREC"):
         assert torch.equal(sparse.buffer(k), dense.buffer(k)), k
