@@ -38,9 +38,9 @@ struct rt_env {
   cudaEvent_t ev_fork = nullptr;
   int raster_ctas = 32, raster_unroll = 2;  // dense rasteriser: CTAs per SM (grid cap), chunks in flight per thread
   bool sparse = true;                       // RT_B200_RASTER=dense selects the dense (LSU) rasteriser
-  int sparse_ctas = 4;                      // k_raster_sparse_lsu: CTAs (8 warp pipelines each) per SM in the grid (2 resident)
+  int sparse_ctas = 24;                     // k_raster_sparse_lsu: CTAs (8 warp pipelines each) per SM in the grid (2 resident)
   bool sparse_lsu = true;                   // RT_B200_RASTER=sparse_tma selects the bulk-store variant
-  int sparse_hints = 3;                     // bit 0: evict-first bulk stores, bit 1: evict-last record loads
+  int sparse_hints = 19;                    // bit 0/1: TMA variant L2 hints; bit 4: plain st.global (else .cs) in the LSU variant
 };
 
 namespace {
@@ -135,9 +135,9 @@ int launch_raster(rt_env* h, float* obs_maps, cudaStream_t st) {
     long long nb = (long long)h->n_sm * h->sparse_ctas;
     if (nb * kSlWarps > d.E) nb = (d.E + kSlWarps - 1) / kSlWarps;
     if (h->lut_in_smem)
-      k_raster_sparse_lsu<true><<<(unsigned)nb, kSlThreads, smb, st>>>(d, obs_maps);
+      k_raster_sparse_lsu<true><<<(unsigned)nb, kSlThreads, smb, st>>>(d, obs_maps, h->sparse_hints & 16);
     else
-      k_raster_sparse_lsu<false><<<(unsigned)nb, kSlThreads, smb, st>>>(d, obs_maps);
+      k_raster_sparse_lsu<false><<<(unsigned)nb, kSlThreads, smb, st>>>(d, obs_maps, h->sparse_hints & 16);
   } else if (h->sparse) {
     const size_t smb = raster_sparse_smem_bytes(d.cells, d.rec_prefix, h->lut_in_smem ? d.cap + 1 : 0);
     long long nb = (long long)h->n_sm;  // 16 tiles fill an SM's shared memory: one persistent CTA each
@@ -241,7 +241,7 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
   size_t off[RT_BUF__COUNT];
   for (int i = 0; i < RT_BUF__COUNT; ++i) off[i] = cv.take(sz[i]);
   const size_t o_act = cv.take(E * A * 4), o_xy = cv.take(E * A * 8), o_rw = cv.take(E * A * 4),
-               o_dn = cv.take(E * A), o_mask = cv.take(E), o_for = cv.take(8);
+               o_dn = cv.take(E * A), o_mask = cv.take(E), o_for = cv.take(16);
   h->slab_bytes = cv.off;
   if (cudaMalloc(&h->slab, h->slab_bytes) != cudaSuccess) {
     rt_note_cuda_error(cudaGetLastError(), "cudaMalloc(slab)");

@@ -594,6 +594,10 @@ __device__ __forceinline__ uint4 ld_cg_u4(const void* p) {  // data written earl
                : "memory");
   return r;
 }
+__device__ __forceinline__ void st_plain_f4(float* p, float4 v) {
+  asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ void st_stream_f4(float* p, float4 v) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
@@ -822,7 +826,7 @@ __host__ __device__ inline size_t raster_sl_smem_bytes(int cells, int lut_entrie
 
 template <bool kLutInSmem>
 __global__ void __launch_bounds__(kSlThreads)
-k_raster_sparse_lsu(const EnvDev d, float* __restrict__ out) {
+k_raster_sparse_lsu(const EnvDev d, float* __restrict__ out, int plain_stores) {
   extern __shared__ __align__(16) unsigned char sm[];
   const int cells = d.cells, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   float* tile = reinterpret_cast<float*>(sm + (size_t)w * cells * 12);
@@ -835,6 +839,9 @@ k_raster_sparse_lsu(const EnvDev d, float* __restrict__ out) {
   __syncthreads();  // table staged (the only CTA-wide barrier)
   const float* lut = kLutInSmem ? s_lut : d.lut;
 
+  // Static strided assignment: warp gw takes envs gw, gw + n_warps, ...  The grid is deliberately MANY
+  // short-lived CTAs (24 per SM, 2 resident): measured best — persistent CTAs leave a tail of stragglers,
+  // and handing envs out through one atomic counter serialises on that address (profiles/r01u, r01v).
   const long long n_warps = (long long)gridDim.x * kSlWarps;
   const long long gw = (long long)blockIdx.x * kSlWarps + w;
   auto load4 = [&](long long e, uint2 (&r)[4]) {  // slots lane, lane+32, lane+64, lane+96 of env e
@@ -845,13 +852,20 @@ k_raster_sparse_lsu(const EnvDev d, float* __restrict__ out) {
       r[m] = j < d.rec_stride ? p[j] : make_uint2(0u, 0u);
     }
   };
-  uint2 nxt[4] = {make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u)};
-  if (gw < d.E) load4(gw, nxt);
+  // records are prefetched two envs ahead (one env's compose + stream-out is much shorter than a DRAM
+  // round trip)
+  uint2 nx1[4] = {make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u)};
+  uint2 nx2[4] = {make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u)};
+  if (gw < d.E) load4(gw, nx1);
+  if (gw + n_warps < d.E) load4(gw + n_warps, nx2);
   for (long long e = gw; e < d.E; e += n_warps) {
     uint2 cur[4];
 #pragma unroll
-    for (int m = 0; m < 4; ++m) cur[m] = nxt[m];
-    if (e + n_warps < d.E) load4(e + n_warps, nxt);  // next env's records fly while this one is composed
+    for (int m = 0; m < 4; ++m) {
+      cur[m] = nx1[m];
+      nx1[m] = nx2[m];
+    }
+    if (e + 2 * n_warps < d.E) load4(e + 2 * n_warps, nx2);
     const int nv = (int)__shfl_sync(0xffffffffu, cur[0].x, 0);
     // agent cells: slots 1 and 2 (lanes 1, 2) hold 8 x uint16
     const uint32_t w1x = __shfl_sync(0xffffffffu, cur[0].x, 1), w1y = __shfl_sync(0xffffffffu, cur[0].y, 1);
@@ -880,7 +894,10 @@ k_raster_sparse_lsu(const EnvDev d, float* __restrict__ out) {
     }
     __syncwarp();
     float* o = out + (size_t)e * 3 * cells;
-    for (int i = lane; i < n4; i += 32) st_stream_f4(o + 4 * i, reinterpret_cast<const float4*>(tile)[i]);
+    if (plain_stores)
+      for (int i = lane; i < n4; i += 32) st_plain_f4(o + 4 * i, reinterpret_cast<const float4*>(tile)[i]);
+    else
+      for (int i = lane; i < n4; i += 32) st_stream_f4(o + 4 * i, reinterpret_cast<const float4*>(tile)[i]);
     __syncwarp();
     // clear exactly what was set
     if (acell != 0xffff) tile[acell] = 0.0f;
