@@ -770,8 +770,7 @@ k_raster_sparse(const EnvDev d, float* __restrict__ out, int hints) {
     else
       bulk_g2s(recs + (size_t)s * pre_bytes, d.vrec + e * d.rec_stride, pre_bytes, full + s);
   };
-  const bool x_nocompose = hints & 4, x_noload = hints & 8;  // experiment knobs (profiles/r01p): not for use
-  if (lane == 0 && !x_noload)
+  if (lane == 0)
     for (int k = 0; k < kSpStages && k < n_mine; ++k) issue_load(k);
 
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -783,18 +782,17 @@ k_raster_sparse(const EnvDev d, float* __restrict__ out, int hints) {
     // the bulk store that last read this tile (kSpStages envs ago) must have finished reading it
     if (lane == 0 && k >= kSpStages) bulk_wait_read<kSpStages - 1>();
     __syncwarp();
-    if (!x_nocompose)
-      for (int i = lane; i < (cells * 3) >> 2; i += 32) reinterpret_cast<float4*>(tile)[i] = z4;
-    if (!x_noload) mbar_wait(full + s, (uint32_t)((k / kSpStages) & 1));  // record prefix has landed
+    for (int i = lane; i < (cells * 3) >> 2; i += 32) reinterpret_cast<float4*>(tile)[i] = z4;
+    mbar_wait(full + s, (uint32_t)((k / kSpStages) & 1));  // record prefix has landed
     __syncwarp();  // zeroing by all lanes is ordered before any lane's scatter
-    const int nv = (x_nocompose || x_noload) ? 0 : (int)rec[0].x;
+    const int nv = (int)rec[0].x;
     for (int i = lane; i < nv; i += 32) {
       const uint2 r = (3 + i < d.rec_prefix) ? rec[3 + i] : d.vrec[e * d.rec_stride + 3 + i];
       const int cell = (int)(r.x & 0xffffu);
       tile[cells + cell] = __uint_as_float(r.y);
       tile[2 * cells + cell] = lut[r.x >> 16];
     }
-    if (lane < RT_MAX_AGENTS && !x_nocompose && !x_noload) {
+    if (lane < RT_MAX_AGENTS) {
       const uint32_t c = reinterpret_cast<const uint16_t*>(rec + 1)[lane];
       if (c != 0xffffu) tile[c] = 1.0f;
     }
@@ -806,7 +804,7 @@ k_raster_sparse(const EnvDev d, float* __restrict__ out, int hints) {
       else
         bulk_s2g(out + e * 3 * (size_t)cells, tile, tile_bytes);
       bulk_commit();
-      if (k + kSpStages < n_mine && !x_noload) issue_load(k + kSpStages);
+      if (k + kSpStages < n_mine) issue_load(k + kSpStages);
     }
   }
   if (lane == 0) bulk_wait_all();
