@@ -84,6 +84,17 @@ _BUF_SPEC = {
 _ITEMSIZE = {"int32": 4, "float64": 8, "float32": 4, "uint16": 2, "uint8": 1}
 
 
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL_CTX = _NullCtx()
+
+
 class BatchedRadSearchEnv:
     """E independent radiation-search envs x A agents, resident on one GPU."""
 
@@ -112,6 +123,9 @@ class BatchedRadSearchEnv:
         # host-path outputs (pinned, so the C ABI copies straight into them)
         self._h_xy = self._h_rw = self._h_dn = None
         self._inj = None
+        self._rollout = None
+        self._views: Dict[str, Any] = {}   # zero-copy tensor views of the handle's arrays, built once
+        self._info_dev: Optional[Dict[str, Any]] = None
 
     # -- plumbing ------------------------------------------------------------------------------
     def _stream(self) -> int:
@@ -138,6 +152,12 @@ class BatchedRadSearchEnv:
 
     def buffer(self, name: str):
         """Zero-copy CUDA tensor view of one state array (rt_buf) — get_state / set_state."""
+        v = self._views.get(name)
+        if v is None:
+            v = self._views[name] = self._make_view(name)
+        return v
+
+    def _make_view(self, name: str):
         torch = self._torch
         ptr, nbytes = C.c_void_p(), C.c_size_t()
         _lib.check(self._L.rt_env_buffer(self._h, _lib.BUF[name], C.byref(ptr), C.byref(nbytes)), name)
@@ -224,10 +244,19 @@ class BatchedRadSearchEnv:
         assert m.numel() == self.E * 3 * self.G * self.G
         return m, m.data_ptr()
 
-    def _info(self, xy) -> Dict[str, Any]:
-        # the reference's oracle view {agent, target, distance} (simple_gridworld.py:192-195)
-        return {"agent": xy, "target": self.buffer("SRC_XY"), "distance": self.buffer("PREV_DIST"),
-                "count": self.buffer("LAST_COUNT"), "maps": self.obs_maps}
+    def _info(self, xy, maps) -> Dict[str, Any]:
+        # the reference's oracle view {agent, target, distance} (simple_gridworld.py:192-195); the values
+        # are views of persistent device arrays, so the dict is built once and only `maps` changes
+        if self._info_dev is None:
+            self._info_dev = {"agent": xy, "target": self.buffer("SRC_XY"), "distance": self.buffer("PREV_DIST"),
+                              "count": self.buffer("LAST_COUNT"), "maps": maps}
+        self._info_dev["maps"] = maps
+        return self._info_dev
+
+    def _on_device(self):
+        """Context that makes this env's GPU current — a no-op object when it already is."""
+        t = self._torch
+        return _NULL_CTX if t.cuda.current_device() == self.device.index else t.cuda.device(self.device)
 
     # -- Gymnasium protocol --------------------------------------------------------------------
     def reset(self, seed: Optional[int] = None, options: Optional[Dict] = None, mask=None, out_maps=None,
@@ -235,7 +264,7 @@ class BatchedRadSearchEnv:
         """SimpleGrid.reset (simple_gridworld.py:114-129), batched; ``mask`` selects envs."""
         torch = self._torch
         maps, mptr = self._maps_ptr(out_maps)
-        with torch.cuda.device(self.device):
+        with self._on_device():
             if host or isinstance(mask, np.ndarray):
                 hxy, _, _ = self._host_bufs()
                 mk = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
@@ -248,20 +277,20 @@ class BatchedRadSearchEnv:
                 mk = mask.to(device=self.device, dtype=torch.uint8).contiguous()
             _lib.check(self._L.rt_env_reset(self._h, None if mk is None else mk.data_ptr(), self.obs_xy.data_ptr(),
                                             mptr, self._stream()), "rt_env_reset")
-        return self.obs_xy, self._info(self.obs_xy)
+        return self.obs_xy, self._info(self.obs_xy, maps)
 
     def step(self, actions, out_maps=None, rasterize: bool = True) -> Tuple[Any, Any, Any, Any, Dict[str, Any]]:
         """SimpleGrid.step (simple_gridworld.py:131-167), batched, plus measurement and map rasterisation
         (``rasterize=False`` leaves the maps to a later ``rasterize()`` call)."""
         torch = self._torch
         maps, mptr = self._maps_ptr(out_maps) if rasterize else (None, None)
-        with torch.cuda.device(self.device):
+        with self._on_device():
             if isinstance(actions, torch.Tensor) and actions.is_cuda:
                 assert actions.dtype == torch.int32 and actions.is_contiguous() and actions.numel() == self.E * self.A
                 _lib.check(self._L.rt_env_step(self._h, actions.data_ptr(), self.obs_xy.data_ptr(), mptr,
                                                self.reward.data_ptr(), self.done.data_ptr(), self._stream()),
                            "rt_env_step")
-                return self.obs_xy, self.reward, self.done, False, self._info(self.obs_xy)
+                return self.obs_xy, self.reward, self.done, False, self._info(self.obs_xy, maps)
             # host path
             if isinstance(actions, torch.Tensor):
                 assert actions.dtype == torch.int32 and actions.is_contiguous()
@@ -283,6 +312,6 @@ class BatchedRadSearchEnv:
 
     def rasterize(self, out_maps=None):
         maps, mptr = self._maps_ptr(out_maps)
-        with self._torch.cuda.device(self.device):
+        with self._on_device():
             _lib.check(self._L.rt_env_rasterize(self._h, mptr, self._stream()), "rt_env_rasterize")
         return maps
