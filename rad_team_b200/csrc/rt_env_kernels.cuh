@@ -291,25 +291,29 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
     if (act < 1 || act > 4) atomicOr(&s.skip[le], RT_FLAG_BAD_ACTION);  // simple_gridworld.py:138
   }
 
-  // a == 0 threads own the per-env statistics; start their loads now.  (Packing the owners into the
-  // first warps was measured SLOWER, 0.089 vs 0.077 ms — see profiles/r01h.)
+  // Per-env statistics are owned by the FIRST n_valid threads of the CTA (thread i <-> env e0 + i): the
+  // sequential chain at the end is pure arithmetic + stores (the list walks happen in the agents' own
+  // threads), so it runs best in fully populated warps.  Start the owners' loads now.
   WelfordState w;
   double emx = 0.0, emn = 0.0, src_int = 0.0, bkg = 0.0;
-  int episode = 0, nv = 0;
+  int episode = 0, nv = 0, tick3 = 0;
   if (valid) {
     src_int = d.src_int[e];
     bkg = d.bkg[e];
     episode = d.episode[e];
-    if (a == 0) {
-      const double2* wp = reinterpret_cast<const double2*>(d.welford + (size_t)e * 6);
-      const double2 w0 = wp[0], w1 = wp[1], w2 = wp[2];
-      w.mean = w0.x; w.m2 = w0.y; w.var = w1.x; w.sd = w1.y; w.zmax = w2.x; w.zmin = w2.y;
-      w.count = d.welford_n[e];
-      const double2 mm = reinterpret_cast<const double2*>(d.est_mm)[e];
-      emx = mm.x;
-      emn = mm.y;
-      nv = (int)d.vrec[(size_t)e * d.rec_stride].x;
-    }
+  }
+  const bool owner = t < n_valid;
+  const int e3 = e0 + t;
+  if (owner) {
+    const double2* wp = reinterpret_cast<const double2*>(d.welford + (size_t)e3 * 6);
+    const double2 w0 = wp[0], w1 = wp[1], w2 = wp[2];
+    w.mean = w0.x; w.m2 = w0.y; w.var = w1.x; w.sd = w1.y; w.zmax = w2.x; w.zmin = w2.y;
+    w.count = d.welford_n[e3];
+    const double2 mm = reinterpret_cast<const double2*>(d.est_mm)[e3];
+    emx = mm.x;
+    emn = mm.y;
+    nv = (int)d.vrec[(size_t)e3 * d.rec_stride].x;
+    tick3 = d.tick[e3];
   }
 
   mbar_wait(s.bar, 0);  // geometry of every env of this CTA has landed in shared memory
@@ -414,12 +418,13 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
   __syncthreads();  // readings and estimates of all agents are in shared memory
 
   // ---- K4a: the env's sequential statistics -------------------------------------------------------
-  if (valid && a == 0) {
-    if (skip) {
-      atomicOr(&d.flags[e], skip);
-      atomicOr(d.step_flags, skip);
+  if (owner) {
+    const int skip3 = s.skip[t];
+    if (skip3) {
+      atomicOr(&d.flags[e3], skip3);
+      atomicOr(d.step_flags, skip3);
     } else {
-      stats_chain(d, s, e, le, tick, w, emx, emn, nv);
+      stats_chain(d, s, e3, t, tick3, w, emx, emn, nv);
     }
   }
 }
