@@ -131,13 +131,12 @@ void launch_raster_vec(rt_env* h, float* obs_maps, cudaStream_t st) {
 int launch_raster(rt_env* h, float* obs_maps, cudaStream_t st) {
   const EnvDev& d = h->dev;
   if (h->sparse && h->sparse_lsu) {
-    const size_t smb = raster_sl_smem_bytes(d.cells, h->lut_in_smem ? d.cap + 1 : 0);
+    // visit-table lookups are rare here (a few dozen per env), so the table is read through L1 from global
+    // memory: staging it in shared memory per CTA (+ a CTA barrier) was measured slower (profiles/r02a)
+    const size_t smb = raster_sl_smem_bytes(d.cells, 0);
     long long nb = (long long)h->n_sm * h->sparse_ctas;
     if (nb * kSlWarps > d.E) nb = (d.E + kSlWarps - 1) / kSlWarps;
-    if (h->lut_in_smem)
-      k_raster_sparse_lsu<true><<<(unsigned)nb, kSlThreads, smb, st>>>(d, obs_maps, h->sparse_hints & 16);
-    else
-      k_raster_sparse_lsu<false><<<(unsigned)nb, kSlThreads, smb, st>>>(d, obs_maps, h->sparse_hints & 16);
+    k_raster_sparse_lsu<false><<<(unsigned)nb, kSlThreads, smb, st>>>(d, obs_maps, h->sparse_hints & 16);
   } else if (h->sparse) {
     const size_t smb = raster_sparse_smem_bytes(d.cells, d.rec_prefix, h->lut_in_smem ? d.cap + 1 : 0);
     long long nb = (long long)h->n_sm;  // 16 tiles fill an SM's shared memory: one persistent CTA each
