@@ -94,7 +94,10 @@ typedef struct rt_env_cfg {
 
 /* Names for rt_env_buffer(): raw device views of the handle's state, for
  * checkpoint / deterministic replay (get_state / set_state) and parity tests.
- * Shapes are in the comments; all arrays are dense row-major. */
+ * Shapes are in the comments; all arrays are dense row-major.  The arrays are
+ * mutually consistent views of one state (e.g. VREC repeats the agents' cells
+ * and the visited cells of VISIT / INTENSITY for the rasteriser): restore a
+ * snapshot by copying ALL of them back, do not edit one in isolation. */
 typedef enum rt_buf {
   RT_BUF_AGENT_XY = 0,   /* int32  [E][A][2]                               */
   RT_BUF_PREV_DIST = 1,  /* int32  [E][A]   agent_previous_dist (L1)       */

@@ -133,6 +133,8 @@ class BatchedRadSearchEnv:
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
+            self._views.clear()      # the views alias memory the handle is about to free
+            self._info_dev = None
             self._L.rt_env_destroy(self._h)
             self._h = C.c_void_p()
 

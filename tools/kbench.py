@@ -7,6 +7,7 @@ Prints one JSON object.
 """
 import argparse
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -70,7 +71,10 @@ def main():
     for t in range(30):
         env.step(acts[t])
     ms = timeit(lambda: env.rasterize(), args.reps)
-    out["k_raster_vec"] = {"ms": ms, "gbs": E * 18432 / ms / 1e6, "frac": E * 18432 / ms / 1e6 / peak}
+    dense = os.environ.get("RT_B200_RASTER", "") == "dense"
+    rb = 18432 if dense else 12288 + 1024  # bytes per env: dense maps re-read, or record prefix only
+    out["k_raster_vec"] = {"kernel": "k_raster_vec" if dense else "k_raster_sparse*", "bytes_per_env": rb, "ms": ms,
+                           "gbs": E * rb / ms / 1e6, "frac": E * rb / ms / 1e6 / peak}
     state = {"t": 30}
 
     def st(raster):
@@ -82,7 +86,7 @@ def main():
     ms = timeit(lambda: st(False), 60)
     out["k_step"] = {"ms": ms, "agent_steps_per_s": E * args.agents / ms * 1e3}
     ms = timeit(lambda: st(True), 60)
-    b = E * (18432 + args.agents * 254)
+    b = E * (rb + args.agents * 254)
     out["step_group"] = {"ms": ms, "gbs": b / ms / 1e6, "frac": b / ms / 1e6 / peak,
                             "agent_steps_per_s": E * args.agents / ms * 1e3}
     ms = timeit(lambda: env.reset(), 10)
