@@ -79,8 +79,8 @@ def main():
     act = torch.empty((T, E, A), dtype=torch.int64, device=dev)
     logp = torch.empty((T, E, A), dtype=torch.float32, device=dev)
     val = torch.empty((T + 1, E, A), dtype=torch.float32, device=dev)
-    rew = torch.empty((T, E, A), dtype=torch.float32, device=dev)
-    dn = torch.empty((T, E, A), dtype=torch.float32, device=dev)
+    rew = torch.empty((T, E, A), dtype=torch.int32, device=dev)    # written by the env, slot by slot
+    dn = torch.empty((T, E, A), dtype=torch.uint8, device=dev)
     readings = torch.zeros((120, E, A), dtype=torch.float32, device=dev)
     env.set_rollout(readings)
     moments = RunningMoments()
@@ -102,13 +102,11 @@ def main():
             a = dist.sample()
             act[t], logp[t], val[t] = a, dist.log_prob(a), v.float()
             a1.record()
-            x, r, d, _, info = env.step((a + 1).to(torch.int32).contiguous(), out_maps=obs[t + 1])
-            xy[t + 1].copy_(x)
-            rew[t].copy_(r)
-            dn[t].copy_(d)
-            cnt = info["count"].float()
-            rd[t + 1] = (cnt - moments.state[1].float()) / torch.clamp(
-                torch.sqrt(moments.state[2] / torch.clamp(moments.state[0] - 1, min=1.0)).float(), min=1.0)
+            # the env writes observation maps, positions, rewards and done flags straight into the
+            # rollout buffer's slots; the step's readings land in row `tick` of the readings sink
+            env.step((a + 1).to(torch.int32), out_maps=obs[t + 1], out_xy=xy[t + 1], out_reward=rew[t],
+                     out_done=dn[t])
+            moments.standardize(readings[steps_in_episode], out=rd[t + 1])   # (count - mean) / max(std, 1)
             a2.record()
             p_pairs.append((a0, a1))
             e_pairs.append((a1, a2))
@@ -124,10 +122,10 @@ def main():
         with torch.no_grad(), torch.autocast("cuda", dtype=amp, enabled=amp != torch.float32):
             _, v_last = model(obs[T], xy[T], rd[T])
         val[T] = v_last.float()
-        adv = torch.zeros_like(rew)
+        adv = torch.zeros((T, E, A), dtype=torch.float32, device=dev)
         last = torch.zeros((E, A), device=dev)
         for t in reversed(range(T)):   # GAE(0.99, 0.95); `done` is informational in the reference (no auto-reset)
-            delta = rew[t] + 0.99 * val[t + 1] - val[t]
+            delta = rew[t].float() + 0.99 * val[t + 1] - val[t]
             last = delta + 0.99 * 0.95 * last
             adv[t] = last
         ret = adv + val[:T]
@@ -152,7 +150,7 @@ def main():
         u = u0.elapsed_time(u1)
         log.append({"iter": it, "env_ms_per_step": e, "policy_ms_per_step": p, "update_ms": u,
                     "env_fraction_of_rollout_step": e / (e + p),
-                    "env_fraction_of_iteration": e * T / (e * T + p * T + u), "loss": float(loss)})
+                    "env_fraction_of_iteration": e * T / (e * T + p * T + u), "loss": float(loss.detach())})
         obs[0].copy_(obs[T]); xy[0].copy_(xy[T]); rd[0].copy_(rd[T])
     if rank == 0:
         print(json.dumps({"config": {"envs_per_gpu": E, "agents": A, "horizon": T, "gpus": world, "dtype": args.dtype},

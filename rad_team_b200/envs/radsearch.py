@@ -281,18 +281,28 @@ class BatchedRadSearchEnv:
                                             mptr, self._stream()), "rt_env_reset")
         return self.obs_xy, self._info(self.obs_xy, maps)
 
-    def step(self, actions, out_maps=None, rasterize: bool = True) -> Tuple[Any, Any, Any, Any, Dict[str, Any]]:
+    def step(self, actions, out_maps=None, rasterize: bool = True, out_xy=None, out_reward=None,
+             out_done=None) -> Tuple[Any, Any, Any, Any, Dict[str, Any]]:
         """SimpleGrid.step (simple_gridworld.py:131-167), batched, plus measurement and map rasterisation
-        (``rasterize=False`` leaves the maps to a later ``rasterize()`` call)."""
+        (``rasterize=False`` leaves the maps to a later ``rasterize()`` call).  On the device path
+        ``out_xy`` (int32 [E,A,2]), ``out_reward`` (int32 [E,A]) and ``out_done`` (uint8 [E,A]) may name
+        caller-owned CUDA tensors — e.g. slots of a rollout buffer — to be written instead of the env's own."""
         torch = self._torch
         maps, mptr = self._maps_ptr(out_maps) if rasterize else (None, None)
         with self._on_device():
             if isinstance(actions, torch.Tensor) and actions.is_cuda:
                 assert actions.dtype == torch.int32 and actions.is_contiguous() and actions.numel() == self.E * self.A
-                _lib.check(self._L.rt_env_step(self._h, actions.data_ptr(), self.obs_xy.data_ptr(), mptr,
-                                               self.reward.data_ptr(), self.done.data_ptr(), self._stream()),
-                           "rt_env_step")
-                return self.obs_xy, self.reward, self.done, False, self._info(self.obs_xy, maps)
+                xy = self.obs_xy if out_xy is None else out_xy
+                rw = self.reward if out_reward is None else out_reward
+                dn = self.done if out_done is None else out_done
+                for t_, dt_, n_ in ((xy, torch.int32, 2), (rw, torch.int32, 1), (dn, torch.uint8, 1)):
+                    assert t_.is_cuda and t_.dtype == dt_ and t_.is_contiguous() and t_.numel() == self.E * self.A * n_
+                _lib.check(self._L.rt_env_step(self._h, actions.data_ptr(), xy.data_ptr(), mptr, rw.data_ptr(),
+                                               dn.data_ptr(), self._stream()), "rt_env_step")
+                info = self._info(self.obs_xy, maps)
+                if out_xy is not None:
+                    info = dict(info, agent=xy)
+                return xy, rw, dn, False, info
             # host path
             if isinstance(actions, torch.Tensor):
                 assert actions.dtype == torch.int32 and actions.is_contiguous()
