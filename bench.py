@@ -362,6 +362,33 @@ def run_ours(args, rank, world, local_rank):
                                "achieved": (raster_bytes + step_bytes) / (fused_ms * 1e-3) / 1e9,
                                "frac": (raster_bytes + step_bytes) / (fused_ms * 1e-3) / 1e9 / peak}}
 
+    # ---- K4b (normalisation kernels) on a rollout-sized buffer in the HBM regime, rank 0 only -----------
+    k4 = None
+    if rank == 0:
+        nbuf = 256 * 1024 * 1024  # fp32 readings = 1 GiB >> 126 MB L2
+        xb = torch.poisson(torch.full((nbuf,), 200.0, device=dev))
+        yb = torch.empty_like(xb)
+        mm = RunningMoments()
+
+        def t_ev(fn, reps=10):
+            for _ in range(3):
+                fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+
+        mu, ms_ = t_ev(lambda: mm.update(xb)), t_ev(lambda: mm.standardize(xb, out=yb))
+        k4 = {"buffer": "1 GiB fp32 readings (HBM regime)",
+              "k_moments_update": {"ms": mu, "achieved": nbuf * 4 / mu / 1e6, "frac": nbuf * 4 / mu / 1e6 / peak,
+                                   "algorithmic_bytes_per_reading": 4},
+              "k_moments_standardize": {"ms": ms_, "achieved": nbuf * 8 / ms_ / 1e6, "frac": nbuf * 8 / ms_ / 1e6 / peak,
+                                        "algorithmic_bytes_per_reading": 8}}
+        del xb, yb, mm
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -384,6 +411,7 @@ def run_ours(args, rank, world, local_rank):
                        "arithmetic": "fp64 physics/statistics, fp32 geometry and maps, int32 indices/counts"},
             "roofline": roofline,
             "kernels": {"step_ms": fused_ms, "k_step_ms": kstep_ms, "raster_ms": raster_ms},
+            "normalisation_kernels": k4,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "agent-env-steps/s", "h2d_bytes_per_step": E * A * 4,
                     "d2h_bytes_per_step": E * A * 13, "steps": K2,

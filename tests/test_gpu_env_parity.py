@@ -320,3 +320,73 @@ def test_sparse_and_dense_rasterisers_agree(monkeypatch, kw):
     assert np.array_equal(nv, (sparse.buffer("VISIT").cpu().numpy() > 0).sum(1))
     if kw["grid"] == 48:
         assert nv.max() > 125  # the overflow path (records beyond the bulk-copied prefix) was exercised
+
+
+def test_step_is_cuda_graph_capturable():
+    """The device path is pure kernel launches on the caller's stream (no sync, no allocation), so a
+    whole step can be captured once and replayed with new actions written into the same tensor."""
+    import torch
+    from rad_team_b200.envs import BatchedRadSearchEnv
+
+    kw = dict(n_envs=500, n_agents=3, grid=32, max_steps=60, poly_min=1, poly_max=5, seed=31)
+    eager, graphed = BatchedRadSearchEnv(**kw), BatchedRadSearchEnv(**kw)
+    rng = np.random.default_rng(31)
+    acts = torch.as_tensor(rng.integers(1, 5, size=(60, 500, 3)).astype(np.int32), device=eager.device)
+    eager.reset(); graphed.reset()
+    static_act = acts[0].clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):       # warm-up outside capture, as torch recommends
+        graphed.step(static_act)
+    torch.cuda.current_stream().wait_stream(side)
+    eager.step(acts[0])
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        graphed.step(static_act)
+    # the capture itself does not execute: replay for steps 1..59
+    for t in range(1, 60):
+        static_act.copy_(acts[t])
+        g.replay()
+        eager.step(acts[t])
+    torch.cuda.synchronize()
+    assert torch.equal(eager.obs_maps, graphed.obs_maps) and torch.equal(eager.obs_xy, graphed.obs_xy)
+    for k in ("VISIT", "INTENSITY", "WELFORD", "VREC", "TICK", "EP_RETURN"):
+        assert torch.equal(eager.buffer(k), graphed.buffer(k)), k
+    assert graphed.errors() == 0
+
+
+def test_host_abi_with_pageable_buffers_and_host_mask():
+    """rt_env_step_host / rt_env_reset_host called directly through ctypes with plain (pageable) NumPy
+    arrays for every host buffer: the handle's pinned staging path."""
+    import ctypes as C
+
+    import torch
+    from oracle import oracle as O
+    from rad_team_b200 import _lib
+    from rad_team_b200.envs import BatchedRadSearchEnv
+
+    kw = dict(O.DEFAULTS); kw.update(n_envs=40, n_agents=2, grid=16, max_steps=30, poly_min=0, poly_max=2, rect_min=1,
+                                     rect_max=3, seed=32)
+    g, o = BatchedRadSearchEnv(**kw), O.OracleEnv(**kw)
+    L, st = _lib.lib(), torch.cuda.current_stream().cuda_stream
+    xy = np.zeros((40, 2, 2), np.int32); rew = np.zeros((40, 2), np.int32); done = np.zeros((40, 2), np.uint8)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    _lib.check(L.rt_env_reset_host(g._h, None, p(xy), g.obs_maps.data_ptr(), st))
+    xy_o, m_o = o.reset()
+    assert np.array_equal(xy, xy_o) and np.array_equal(g.obs_maps.cpu().numpy(), m_o)
+    rng = np.random.default_rng(32)
+    for t in range(20):
+        act = rng.integers(1, 5, size=(40, 2)).astype(np.int32)
+        _lib.check(L.rt_env_step_host(g._h, p(act), p(xy), p(rew), p(done), g.obs_maps.data_ptr(), st))
+        xy_o, m_o, rew_o, done_o = o.step(act)
+        assert np.array_equal(xy, xy_o) and np.array_equal(rew, rew_o) and np.array_equal(done, done_o)
+        assert np.array_equal(g.obs_maps.cpu().numpy(), m_o)
+        if t == 9:
+            mask = (rng.random(40) < 0.4).astype(np.uint8)
+            _lib.check(L.rt_env_reset_host(g._h, p(mask), p(xy), g.obs_maps.data_ptr(), st))
+            xy_o, m_o = o.reset(mask=mask)
+            assert np.array_equal(xy, xy_o) and np.array_equal(g.obs_maps.cpu().numpy(), m_o)
+    act = np.ones((40, 2), np.int32); act[7, 1] = 9
+    assert L.rt_env_step_host(g._h, p(act), p(xy), p(rew), p(done), None, st) == _lib.RT_ERR_BAD_ACTION
+    o.step(act, maps=False)
+    assert np.array_equal(g.buffer("TICK").cpu().numpy(), o.export("TICK"))  # env 7 voided, the rest advanced
