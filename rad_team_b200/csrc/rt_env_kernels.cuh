@@ -1,15 +1,17 @@
 // rt_env_kernels.cuh — the environment kernels of librt_b200.so (sm_100a).
 //
-//   k_step      K1+K2+K4a  motion / collision / reward (simple_gridworld.py:131-167),
-//               measurement (inverse square, line of sight against obstruction edges
-//               staged in shared memory by bulk async copies, Philox Poisson), then the
-//               per-env observation statistics (estimator.py:31-70 -> standardize.py:46-93
-//               -> normalize.py:25-55) and the map cell updates.
-//   k_raster    K3  location / intensity / visit maps -> caller's [E][3][G][G] tensor.
-//   k_reset_*   K5  masked episode reset + scenario generation.
+//   k_step               K1+K2+K4a  motion / collision / reward (simple_gridworld.py:131-167), measurement
+//                        (inverse square, line of sight against obstruction edges staged in shared memory
+//                        by bulk async copies, Philox Poisson), each agent's estimator update
+//                        (estimator.py:31-70), then per env the sequential Welford -> normalise chain
+//                        (standardize.py:46-93 -> normalize.py:25-55) and the map / record updates.
+//   k_raster_sparse_lsu  K3 (default)  visited-cell records -> shared-memory tile -> coalesced 16 B stores
+//   k_raster_sparse      K3  the same through the bulk-copy (TMA) engine
+//   k_raster_vec / _any  K3  from the dense maps (vectorised / any grid side)
+//   k_reset_state, k_zero_maps   K5  masked episode reset + scenario generation.
 //
-// HBM layout is structure-of-arrays over envs so that neighbouring threads touch
-// neighbouring addresses; the reading log is time-major [T*A][E] for the same reason.
+// HBM layout is structure-of-arrays over envs so that neighbouring threads touch neighbouring addresses;
+// the reading log is time-major [T*A][E] for the same reason.
 #pragma once
 #include <math_constants.h>
 
