@@ -82,10 +82,17 @@ k_episode_stats(const int32_t* __restrict__ ep_return, const uint8_t* __restrict
     len += __shfl_down_sync(0xffffffffu, len, off);
     dn += __shfl_down_sync(0xffffffffu, dn, off);
   }
+  __shared__ long long s_part[3][8];
   if ((threadIdx.x & 31) == 0) {
-    atomicAdd(out + 0, (double)ret);
-    atomicAdd(out + 1, (double)len);
-    atomicAdd(out + 2, (double)dn);
+    s_part[0][threadIdx.x >> 5] = ret;
+    s_part[1][threadIdx.x >> 5] = len;
+    s_part[2][threadIdx.x >> 5] = dn;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {  // one atomic per quantity and CTA (per-warp atomics on one address serialise)
+    long long v = 0;
+    for (int i = 0; i < 8; ++i) v += s_part[threadIdx.x][i];
+    atomicAdd(out + threadIdx.x, (double)v);
   }
 }
 
