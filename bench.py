@@ -415,8 +415,9 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "agent-env-steps/s", "h2d_bytes_per_step": E * A * 4,
                     "d2h_bytes_per_step": E * A * 13, "steps": K2,
-                    "note": "rt_env_step_host per step: pinned int32 actions up; obs_xy, reward, done down; maps are "
-                            "rasterised into the device-resident CNN input tensor"},
+                    "note": "rt_env_step_host per step: pinned int32 actions cross PCIe every step (k_step reads the mapped "
+                            "buffer in place, no staging copy); obs_xy, reward, done are copied down on an auxiliary "
+                            "stream under the rasteriser; maps are rasterised into the device-resident CNN input tensor"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "error_flags": flags,

@@ -174,10 +174,11 @@ int rt_env_step(rt_env* env, const int32_t* actions_dev, int32_t* obs_xy_dev, fl
 
 /* The same two calls with HOST buffers for everything the reference returns
  * to Python (obs, reward, done); the maps stay on the device (they are the
- * CNN's input tensor).  Pinned caller buffers are used directly, pageable ones
- * go through pinned staging owned by the handle; the results travel back on an
- * internal stream while the rasteriser runs, and the call returns after they
- * have landed.  rt_env_step_host returns RT_ERR_BAD_ACTION when an action was
+ * CNN's input tensor).  Pinned caller buffers are used directly (the step
+ * kernel reads pinned actions in place over PCIe), pageable ones go through
+ * pinned staging owned by the handle; the results travel back on an internal
+ * stream while the rasteriser runs, and the call returns after they have
+ * landed.  rt_env_step_host returns RT_ERR_BAD_ACTION when an action was
  * outside 1..4: the steps of exactly those envs were voided (no state change,
  * as in the reference, which raises before touching state); every other env
  * advanced and all outputs are valid. */

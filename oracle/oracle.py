@@ -122,9 +122,12 @@ class OracleEnv:
         self._inj = None
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().orc_destroy(self._h)
-            self._h = None
+        try:  # may run during interpreter shutdown, when module globals are already gone
+            if getattr(self, "_h", None):
+                lib().orc_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
 
     def set_threads(self, n: int) -> int:
         return lib().orc_set_threads(self._h, n)

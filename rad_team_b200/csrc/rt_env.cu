@@ -37,6 +37,7 @@ struct rt_env {
   cudaStream_t aux = nullptr;  // host path: results travel back here while the rasteriser streams
   cudaEvent_t ev_fork = nullptr;
   int raster_ctas = 32, raster_unroll = 2;  // dense rasteriser: CTAs per SM (grid cap), chunks in flight per thread
+  bool zerocopy = true;                     // host path: k_step reads pinned caller actions in place
   bool sparse = true;                       // RT_B200_RASTER=dense selects the dense (LSU) rasteriser
   int sparse_ctas = 24;                     // k_raster_sparse_lsu: CTAs (8 warp pipelines each) per SM in the grid (2 resident)
   bool sparse_lsu = true;                   // RT_B200_RASTER=sparse_tma selects the bulk-store variant
@@ -62,6 +63,17 @@ bool is_pinned_or_device(const void* p) {
   }
   return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged ||
          at.type == cudaMemoryTypeDevice;
+}
+
+// device-side alias of a pinned / managed / device allocation (nullptr for pageable memory)
+const void* device_alias(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (at.type == cudaMemoryTypeUnregistered) return nullptr;
+  return at.devicePointer;
 }
 
 // {sum of returns, sum of episode lengths, agents that reached the source}: integer partial sums per
@@ -357,6 +369,7 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
     const int v = std::atoi(ev);
     if (v >= 1 && v * cfg->n_agents <= 192) h->epb = v;
   }
+  if (const char* ev = std::getenv("RT_B200_ZEROCOPY")) h->zerocopy = std::atoi(ev) != 0;
   if (const char* ev = std::getenv("RT_B200_RASTER_CTAS")) h->raster_ctas = std::max(1, std::atoi(ev));
   if (const char* ev = std::getenv("RT_B200_RASTER_UNROLL")) h->raster_unroll = std::max(1, std::atoi(ev));
   if (const char* ev = std::getenv("RT_B200_SPARSE_CTAS")) h->sparse_ctas = std::max(1, std::atoi(ev));
@@ -478,15 +491,23 @@ int rt_env_step_host(rt_env* h, const int32_t* actions_host, int32_t* obs_xy_hos
   unsigned char* p_dn = h->pinned + n * 16;
   // Invalid actions are caught on the device: the env's step is voided (the reference raises before any
   // state change, simple_gridworld.py:138) and a flag word travels back with the results.
-  const void* a_src = actions_host;
-  if (!is_pinned_or_device(actions_host)) {
-    std::memcpy(p_act, actions_host, n * 4);
-    a_src = p_act;
+  // Pinned (mapped) caller memory is read by k_step directly over PCIe — no separate H2D copy in front
+  // of the kernel; pageable memory is staged and copied.  RT_B200_ZEROCOPY=0 forces the copy.
+  const int32_t* actions_dev = h->d_actions;
+  const void* alias = h->zerocopy ? device_alias(actions_host) : nullptr;
+  if (alias != nullptr) {
+    actions_dev = static_cast<const int32_t*>(alias);
+  } else {
+    const void* a_src = actions_host;
+    if (!is_pinned_or_device(actions_host)) {
+      std::memcpy(p_act, actions_host, n * 4);
+      a_src = p_act;
+    }
+    RT_CUDA(cudaMemcpyAsync(h->d_actions, a_src, n * 4, cudaMemcpyHostToDevice, st));
   }
-  RT_CUDA(cudaMemcpyAsync(h->d_actions, a_src, n * 4, cudaMemcpyHostToDevice, st));
   RT_CUDA(cudaMemsetAsync(h->dev.step_flags, 0, 4, st));
   // k_step, then the small results travel back on the auxiliary stream WHILE the rasteriser streams
-  int rc = launch_step(h, h->d_actions, h->d_obs_xy, nullptr, h->d_reward, h->d_done, st);
+  int rc = launch_step(h, actions_dev, h->d_obs_xy, nullptr, h->d_reward, h->d_done, st);
   if (rc != RT_OK) return rc;
   RT_CUDA(cudaEventRecord(h->ev_fork, st));
   RT_CUDA(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
