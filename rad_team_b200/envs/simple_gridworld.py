@@ -51,6 +51,15 @@ class SimpleGrid(_Base):
         assert render_mode is None or render_mode in self.metadata["render_modes"]
         self.render_mode = render_mode
         self.reward_range = (-np.inf, np.inf)
+        # spaces as in the reference (:103-104) when gymnasium is importable; plain descriptions otherwise
+        try:
+            from gymnasium import spaces as _sp  # type: ignore
+
+            self.action_space = _sp.MultiDiscrete([a.value for a in Action])
+            self.observation_space = _sp.Box(low=0, high=self.size - 1, shape=(2,), dtype=np.int32)
+        except Exception:  # pragma: no cover - gymnasium is absent from this image
+            self.action_space = {"type": "MultiDiscrete", "nvec": [a.value for a in Action]}
+            self.observation_space = {"type": "Box", "low": 0, "high": self.size - 1, "shape": (2,), "dtype": np.int32}
         cfg = RadSearchConfig(n_envs=1, n_agents=1, grid=int(size), max_steps=int(max_steps), fixed_scenario=1)
         self._env = BatchedRadSearchEnv(cfg)
         self._env.set_scenario(src_xy=np.asarray(terminal, np.int32), src_int=[1e6], bkg=[10.0],
