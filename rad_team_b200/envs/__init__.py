@@ -1,8 +1,9 @@
 """Environments — mirrors the reference's ``src/envs`` package (src/envs/__init__.py:3-6)."""
 from .radsearch import BatchedRadSearchEnv, RadSearchConfig
 from .simple_gridworld import Action, ActionDirectionMap, SimpleGrid
+from .vector import RadSearchVectorEnv
 
-__all__ = ["BatchedRadSearchEnv", "RadSearchConfig", "SimpleGrid", "Action", "ActionDirectionMap"]
+__all__ = ["BatchedRadSearchEnv", "RadSearchConfig", "RadSearchVectorEnv", "SimpleGrid", "Action", "ActionDirectionMap"]
 
 try:  # same registry id as the reference when gymnasium is present
     from gymnasium.envs.registration import register  # type: ignore

@@ -310,3 +310,42 @@ def test_estimator_runs_vs_reference(golden_math):
         k0 = tuple(run["rows"][0][0])
         want = [fh(r[1]) for r in run["rows"][:150] if tuple(r[0]) == k0]
         assert [float(x) for x in e.get_buffer(k0)] == want
+
+
+# ---- Gymnasium-style vector adapter -----------------------------------------------
+def test_vector_env_adapter_autoreset_and_shapes():
+    from oracle import oracle as O
+    from rad_team_b200.envs import RadSearchVectorEnv
+
+    kw = dict(poly_min=0, poly_max=2, rect_min=1, rect_max=3, seed=41)
+    venv = RadSearchVectorEnv(num_envs=64, n_agents=2, grid=8, max_steps=12, **kw)
+    ok = dict(O.DEFAULTS); ok.update(n_envs=64, n_agents=2, grid=8, max_steps=12, **kw)
+    orc = O.OracleEnv(**ok)
+    obs, info = venv.reset()
+    xy_o, m_o = orc.reset()
+    assert obs.shape == (64, 2, 2) and obs.dtype == np.int32 and np.array_equal(obs, xy_o)
+    assert np.array_equal(info["maps"].cpu().numpy(), m_o)
+    rng = np.random.default_rng(41)
+    saw_trunc = saw_term = False
+    tick = np.zeros(64, np.int32)
+    for t in range(40):
+        act = rng.integers(1, 5, size=(64, 2))
+        obs, rew, term, trunc, info = venv.step(act)
+        xy_o, m_o, rew_o, done_o = orc.step(act.astype(np.int32))
+        tick += 1
+        want_term = done_o.astype(bool).any(1)
+        want_trunc = (tick >= 12) & ~want_term
+        assert np.array_equal(term, want_term) and np.array_equal(trunc, want_trunc)
+        assert rew.shape == (64,) and np.array_equal(rew, rew_o.sum(1)) and np.array_equal(info["agent_reward"], rew_o)
+        fin = want_term | want_trunc
+        if fin.any():
+            assert np.array_equal(info["final_observation"], xy_o) and np.array_equal(info["_final_observation"], fin)
+            xy_o, m_o = orc.reset(mask=fin.astype(np.uint8))
+            tick[fin] = 0
+            saw_trunc |= bool(want_trunc.any()); saw_term |= bool(want_term.any())
+        assert np.array_equal(obs, xy_o)
+        assert np.array_equal(info["maps"].cpu().numpy(), m_o)
+    assert saw_trunc and saw_term
+    with pytest.raises(ValueError, match="is not a valid Action"):
+        venv.step(np.zeros((64, 2), np.int64))
+    venv.close()
