@@ -191,6 +191,14 @@ int rt_env_step_host(rt_env* env, const int32_t* actions_host, int32_t* obs_xy_h
  * rasterise the current state into obs_maps [E][3][G][G]. */
 int rt_env_rasterize(rt_env* env, float* obs_maps_dev, void* stream);
 
+/* Opt-in for loops that hand the SAME obs_maps tensor to every step (inference,
+ * evaluation): when enabled and obs_maps is the tensor this env rasterised
+ * into last time, rt_env_step only rewrites the <= 2A cells per env that the
+ * step changed instead of the whole tensor.  The caller must not have modified
+ * the tensor in between.  A different pointer, a reset, or a step without maps
+ * falls back to a full rasterisation.  Off by default. */
+int rt_env_set_incremental(rt_env* env, int32_t enable);
+
 /* Test hook: replace the counter-based RNG of the Poisson sampler by injected
  * uniforms u [E][A][k_per_agent] (device, doubles in [0,1)); NULL switches
  * back to Philox.  The pointer must stay valid until replaced. */

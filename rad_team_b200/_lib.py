@@ -50,6 +50,7 @@ SYMBOLS = {
     "rt_env_reset_host": (C.c_int, [_vp] * 5),
     "rt_env_step_host": (C.c_int, [_vp] * 7),
     "rt_env_rasterize": (C.c_int, [_vp, _vp, _vp]),
+    "rt_env_set_incremental": (C.c_int, [_vp, _i32]),
     "rt_env_inject_uniforms": (C.c_int, [_vp, _vp, _i32]),
     "rt_env_set_rollout": (C.c_int, [_vp, _vp]),
     "rt_env_episode_stats": (C.c_int, [_vp, _vp, _vp]),

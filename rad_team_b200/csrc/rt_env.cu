@@ -37,6 +37,8 @@ struct rt_env {
   cudaStream_t aux = nullptr;  // host path: results travel back here while the rasteriser streams
   cudaEvent_t ev_fork = nullptr;
   int raster_ctas = 32, raster_unroll = 2;  // dense rasteriser: CTAs per SM (grid cap), chunks in flight per thread
+  bool incremental = false;                 // rt_env_set_incremental: patch the caller's tensor when it is the same as last time
+  const float* last_maps = nullptr;         // tensor that holds this env's latest observation
   bool zerocopy = true;                     // host path: k_step reads pinned caller actions in place
   bool sparse = true;                       // RT_B200_RASTER=dense selects the dense (LSU) rasteriser
   int sparse_ctas = 24;                     // k_raster_sparse_lsu: CTAs (8 warp pipelines each) per SM in the grid (2 resident)
@@ -149,6 +151,7 @@ void launch_raster_vec(rt_env* h, float* obs_maps, cudaStream_t st) {
 
 int launch_raster(rt_env* h, float* obs_maps, cudaStream_t st) {
   const EnvDev& d = h->dev;
+  h->last_maps = obs_maps;
   if (h->sparse && h->sparse_lsu) {
     // visit-table lookups are rare here (a few dozen per env), so the table is read through L1 from global
     // memory: staging it in shared memory per CTA (+ a CTA barrier) was measured slower (profiles/r02a)
@@ -177,15 +180,29 @@ int launch_raster(rt_env* h, float* obs_maps, cudaStream_t st) {
   return RT_OK;
 }
 
+// full rasterisation, or — opted in and handed the tensor that already holds the previous observation —
+// the incremental patch of the cells the step changed
+int raster_or_patch(rt_env* h, float* obs_maps, cudaStream_t st) {
+  const EnvDev& d = h->dev;
+  if (h->incremental && obs_maps == h->last_maps) {
+    k_patch_incremental<<<(unsigned)((d.E + 255) / 256), 256, 0, st>>>(d, obs_maps);
+    h->launches += 1;
+    RT_CUDA_LAUNCH_CHECK();
+    return RT_OK;
+  }
+  return launch_raster(h, obs_maps, st);
+}
+
 int launch_step(rt_env* h, const int32_t* actions, int32_t* obs_xy, float* obs_maps, int32_t* reward,
-                uint8_t* done, cudaStream_t st) {
+                uint8_t* done, cudaStream_t st, bool raster_follows = false) {
   const EnvDev& d = h->dev;
   const int epb = h->epb;
   const unsigned blocks = (unsigned)((d.E + epb - 1) / epb);
   k_step<<<blocks, epb * d.A, step_smem_bytes(epb, d.A), st>>>(d, actions, obs_xy, reward, done);
   h->launches += 1;
   RT_CUDA_LAUNCH_CHECK();
-  if (obs_maps) return launch_raster(h, obs_maps, st);
+  if (obs_maps) return raster_or_patch(h, obs_maps, st);
+  if (!raster_follows) h->last_maps = nullptr;  // a step without rasterisation leaves every tensor stale
   return RT_OK;
 }
 
@@ -196,6 +213,7 @@ int launch_reset(rt_env* h, const uint8_t* mask, int32_t* obs_xy, float* obs_map
   h->launches += 2;
   RT_CUDA_LAUNCH_CHECK();
   if (obs_maps) return launch_raster(h, obs_maps, st);
+  h->last_maps = nullptr;  // state changed without a rasterisation: every tensor is stale
   return RT_OK;
 }
 
@@ -259,7 +277,7 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
   size_t off[RT_BUF__COUNT];
   for (int i = 0; i < RT_BUF__COUNT; ++i) off[i] = cv.take(sz[i]);
   const size_t o_act = cv.take(E * A * 4), o_xy = cv.take(E * A * 8), o_rw = cv.take(E * A * 4),
-               o_dn = cv.take(E * A), o_mask = cv.take(E), o_for = cv.take(16);
+               o_dn = cv.take(E * A), o_mask = cv.take(E), o_for = cv.take(16), o_prev = cv.take(E * 16);
   h->slab_bytes = cv.off;
   if (cudaMalloc(&h->slab, h->slab_bytes) != cudaSuccess) {
     rt_note_cuda_error(cudaGetLastError(), "cudaMalloc(slab)");
@@ -328,6 +346,7 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
   d.rec_prefix = rec_stride < 128 ? rec_stride : 128;  // 1 KB per env covers 125 visited cells; the rest is read directly
   d.rollout = nullptr;
   d.step_flags = h->d_flag_or + 1;
+  d.prev_cells = (uint4*)(base + o_prev);
   d.inj = nullptr;
   d.inj_k = 0;
 
@@ -507,7 +526,7 @@ int rt_env_step_host(rt_env* h, const int32_t* actions_host, int32_t* obs_xy_hos
   }
   RT_CUDA(cudaMemsetAsync(h->dev.step_flags, 0, 4, st));
   // k_step, then the small results travel back on the auxiliary stream WHILE the rasteriser streams
-  int rc = launch_step(h, actions_dev, h->d_obs_xy, nullptr, h->d_reward, h->d_done, st);
+  int rc = launch_step(h, actions_dev, h->d_obs_xy, nullptr, h->d_reward, h->d_done, st, obs_maps_dev != nullptr);
   if (rc != RT_OK) return rc;
   RT_CUDA(cudaEventRecord(h->ev_fork, st));
   RT_CUDA(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
@@ -519,7 +538,7 @@ int rt_env_step_host(rt_env* h, const int32_t* actions_host, int32_t* obs_xy_hos
   int32_t* p_fl = reinterpret_cast<int32_t*>(h->pinned + h->pinned_bytes - 16);
   RT_CUDA(cudaMemcpyAsync(p_fl, h->dev.step_flags, 4, cudaMemcpyDeviceToHost, h->aux));
   if (obs_maps_dev) {
-    rc = launch_raster(h, obs_maps_dev, st);
+    rc = raster_or_patch(h, obs_maps_dev, st);
     if (rc != RT_OK) return rc;
   }
   RT_CUDA(cudaStreamSynchronize(h->aux));
@@ -534,6 +553,13 @@ int rt_env_step_host(rt_env* h, const int32_t* actions_host, int32_t* obs_xy_hos
 int rt_env_rasterize(rt_env* h, float* obs_maps_dev, void* stream) {
   if (!h || !obs_maps_dev) return RT_ERR_BAD_ARG;
   return launch_raster(h, obs_maps_dev, (cudaStream_t)stream);
+}
+
+int rt_env_set_incremental(rt_env* h, int32_t enable) {
+  if (!h) return RT_ERR_BAD_ARG;
+  h->incremental = enable != 0;
+  h->last_maps = nullptr;
+  return RT_OK;
 }
 
 int rt_env_inject_uniforms(rt_env* h, const double* u_dev, int32_t k_per_agent) {

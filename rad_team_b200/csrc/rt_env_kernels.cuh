@@ -60,6 +60,7 @@ struct EnvDev {
   uint8_t* ep_done;    // [E][A]
   float* rollout;      // [T][E][A] readings sink, or nullptr
   int32_t* step_flags; // one word: OR of the RT_FLAG_* that voided an env's step in the CURRENT launch
+  uint4* prev_cells;   // [E] the agents' cells BEFORE the last step (8 x uint16), for the incremental observation update
   const double* inj;
   int inj_k;
 };
@@ -229,6 +230,8 @@ __device__ __forceinline__ void stats_chain(const EnvDev& d, const StepSmem& s, 
     else
       p1 = (p1 & ~(0xffffull << sh)) | (c << sh);
   }
+  const uint2 o1 = rec[1], o2 = rec[2];  // same 32-byte sector as rec[0], already in flight for nv
+  d.prev_cells[e] = make_uint4(o1.x, o1.y, o2.x, o2.y);
   rec[0] = make_uint2((uint32_t)nv, 0u);
   rec[1] = make_uint2((uint32_t)p0, (uint32_t)(p0 >> 32));
   rec[2] = make_uint2((uint32_t)p1, (uint32_t)(p1 >> 32));
@@ -544,6 +547,7 @@ k_reset_state(const EnvDev d, const uint8_t* __restrict__ mask, int32_t* __restr
     rec[0] = make_uint2(0u, 0u);
     rec[1] = make_uint2((uint32_t)p0, (uint32_t)(p0 >> 32));
     rec[2] = make_uint2((uint32_t)p1, (uint32_t)(p1 >> 32));
+    d.prev_cells[e] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
   }
   double2* wp = reinterpret_cast<double2*>(d.welford + (size_t)e * 6);
   wp[0] = make_double2(0.0, 0.0);  // standardize.py:36-44
@@ -921,6 +925,35 @@ k_raster_sparse_lsu(const EnvDev d, float* __restrict__ out, int plain_stores) {
       tile[2 * cells + cell] = 0.0f;
     }
     __syncwarp();
+  }
+}
+
+// K3, incremental form (opt-in, rt_env_set_incremental): when the caller hands back the SAME tensor that
+// holds this env's previous observation, a step changes at most 2A cells per env — the agents' old cells
+// lose their location mark, the new cells get mark, intensity and visit value.  One thread per env.
+__global__ void __launch_bounds__(256)
+k_patch_incremental(const EnvDev d, float* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.E) return;
+  const uint4 pv = d.prev_cells[e];
+  const uint2* rec = d.vrec + (size_t)e * d.rec_stride;
+  const uint2 c1 = rec[1], c2 = rec[2];
+  float* o = out + (size_t)e * 3 * d.cells;
+  const uint32_t prevw[4] = {pv.x, pv.y, pv.z, pv.w}, curw[4] = {c1.x, c1.y, c2.x, c2.y};
+#pragma unroll
+  for (int a = 0; a < RT_MAX_AGENTS; ++a) {  // clear first, mark afterwards: an agent may enter a cell another one left
+    const uint32_t c = (prevw[a >> 1] >> (16 * (a & 1))) & 0xffffu;
+    if (c != 0xffffu) o[c] = 0.0f;
+  }
+#pragma unroll
+  for (int a = 0; a < RT_MAX_AGENTS; ++a) {
+    const uint32_t c = (curw[a >> 1] >> (16 * (a & 1))) & 0xffffu;
+    if (c != 0xffffu) {
+      const size_t m = (size_t)e * d.cells + c;
+      o[c] = 1.0f;
+      o[d.cells + c] = d.inten[m];
+      o[2 * (size_t)d.cells + c] = d.lut[d.visit[m]];
+    }
   }
 }
 

@@ -198,6 +198,13 @@ class BatchedRadSearchEnv:
         with self._torch.cuda.device(self.device):
             _lib.check(self._L.rt_env_set_scenario(self._h, *ptrs), "rt_env_set_scenario")
 
+    def set_incremental(self, enable: bool = True) -> None:
+        """Opt in to incremental observation updates: a step that is handed the same ``obs_maps`` tensor as
+        the previous rasterisation rewrites only the cells the step changed (the caller must not modify
+        the tensor in between).  Meant for inference / evaluation loops; rollout buffers use distinct slots
+        and are always rasterised in full."""
+        _lib.check(self._L.rt_env_set_incremental(self._h, 1 if enable else 0))
+
     def inject_uniforms(self, u) -> None:
         """Test hook: Poisson sampler reads u[E, A, K] instead of Philox (None switches back)."""
         if u is None:

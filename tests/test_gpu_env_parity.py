@@ -390,3 +390,48 @@ def test_host_abi_with_pageable_buffers_and_host_mask():
     assert L.rt_env_step_host(g._h, p(act), p(xy), p(rew), p(done), None, st) == _lib.RT_ERR_BAD_ACTION
     o.step(act, maps=False)
     assert np.array_equal(g.buffer("TICK").cpu().numpy(), o.export("TICK"))  # env 7 voided, the rest advanced
+
+
+def test_incremental_observation_update_matches_full_rasterisation():
+    """Opt-in rt_env_set_incremental: handed the same tensor every step, the env only patches the cells a
+    step changed; the tensor must stay bit-identical to a full rasterisation — across masked resets, a
+    change of target tensor, invalid actions, agents sharing and swapping cells, and the host path."""
+    import torch
+    from rad_team_b200.envs import BatchedRadSearchEnv
+
+    kw = dict(n_envs=400, n_agents=4, grid=8, max_steps=50, poly_min=0, poly_max=2, rect_min=1, rect_max=2, seed=51)
+    full, inc = BatchedRadSearchEnv(**kw), BatchedRadSearchEnv(**kw)
+    inc.set_incremental(True)
+    rng = np.random.default_rng(51)
+    full.reset(); inc.reset()
+    other = torch.zeros_like(inc.obs_maps)
+    l_full = l_inc = 0
+    for t in range(120):
+        a_np = rng.integers(1, 5, size=(400, 4)).astype(np.int32)
+        if t % 11 == 5:
+            a_np[rng.integers(0, 400), rng.integers(0, 4)] = 0                    # voided env
+        act = torch.as_tensor(a_np, device=full.device)
+        l0, l1 = full.launches, inc.launches
+        full.step(act)
+        if t % 17 == 9:                       # a different target tensor: must fall back to a full rasterisation
+            inc.step(act, out_maps=other)
+            assert torch.equal(other, full.obs_maps), t
+            inc.rasterize()                   # bring the env's own tensor up to date again (full)
+        elif t % 13 == 3:                     # host path
+            try:
+                inc.step(a_np)
+            except ValueError:
+                pass
+        else:
+            inc.step(act)
+        l_full += full.launches - l0; l_inc += inc.launches - l1
+        assert torch.equal(inc.obs_maps, full.obs_maps), t
+        if t % 25 == 24:
+            mask = torch.as_tensor((rng.random(400) < 0.5).astype(np.uint8), device=full.device)
+            full.reset(mask=mask); inc.reset(mask=mask)
+            assert torch.equal(inc.obs_maps, full.obs_maps)
+        if t == 49 or t == 99:
+            full.reset(); inc.reset()
+    assert full.errors() == inc.errors()
+    for k in ("VISIT", "INTENSITY", "VREC"):
+        assert torch.equal(full.buffer(k), inc.buffer(k)), k

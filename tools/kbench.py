@@ -89,6 +89,11 @@ def main():
     b = E * (rb + args.agents * 254)
     out["step_group"] = {"ms": ms, "gbs": b / ms / 1e6, "frac": b / ms / 1e6 / peak,
                             "agent_steps_per_s": E * args.agents / ms * 1e3}
+    env.set_incremental(True)   # opt-in: same tensor every step -> only the changed cells are rewritten
+    ms = timeit(lambda: st(True), 60)
+    out["step_group_incremental_obs"] = {"ms": ms, "agent_steps_per_s": E * args.agents / ms * 1e3,
+                                         "note": "opt-in for inference loops; NOT what bench.py measures"}
+    env.set_incremental(False)
     ms = timeit(lambda: env.reset(), 10)
     out["reset_3_kernels_ms"] = ms
     del env
