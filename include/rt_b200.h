@@ -71,7 +71,7 @@ typedef struct rt_estimator rt_estimator; /* per-cell median resampling estimato
 typedef struct rt_env_cfg {
   int32_t n_envs;       /* E: envs owned by this handle (this GPU's shard)        */
   int32_t n_agents;     /* A: 1..RT_MAX_AGENTS                                   */
-  int32_t grid;         /* G: cells per side (reference `size`, default 10)      */
+  int32_t grid;         /* G: cells per side (reference `size`, default 10), 2..255 */
   int32_t max_steps;    /* T: steps per episode; reading log holds T*A entries;
                            T*A must be in [2, 65534]                             */
   int32_t poly_min;     /* obstructions per generated scenario: U{min..max}      */

@@ -241,10 +241,12 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
   *out = nullptr;
   const long long cap = (long long)cfg->max_steps * cfg->n_agents;
   if (cfg->n_envs < 1 || cfg->n_agents < 1 || cfg->n_agents > RT_MAX_AGENTS || cfg->grid < 2 ||
-      cfg->grid > 256 || cfg->max_steps < 1 || cap < 2 || cap > 65534 || cfg->poly_min < 0 ||
+      cfg->grid > 255 || cfg->max_steps < 1 || cap < 2 || cap > 65534 || cfg->poly_min < 0 ||
       cfg->poly_max < cfg->poly_min || cfg->poly_max > RT_MAX_POLYS || cfg->lognorm_step < 1 ||
       !(cfg->cell_pitch_cm > 0.0) || !(cfg->min_dist_cm > 0.0) || !(cfg->transmission >= 0.0) ||
-      (cfg->poly_max > 0 && (cfg->rect_min < 1 || cfg->rect_max < cfg->rect_min)))
+      (cfg->poly_max > 0 && (cfg->rect_min < 1 || cfg->rect_max < cfg->rect_min)) ||
+      !(cfg->src_lo >= 0.0) || !(cfg->src_hi >= cfg->src_lo) || !(cfg->bkg_lo >= 0.0) || !(cfg->bkg_hi >= cfg->bkg_lo) ||
+      !std::isfinite(cfg->src_hi) || !std::isfinite(cfg->bkg_hi))
     return RT_ERR_BAD_ARG;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {

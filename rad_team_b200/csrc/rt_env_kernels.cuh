@@ -137,7 +137,9 @@ __device__ __forceinline__ double list_insert_median(uint2* __restrict__ log, si
   const int k1 = (n - 1) >> 1, k2 = n >> 1;
   int pred = 0, m1 = 0, m2 = 0;
   bool inserted = false;
-  for (int i = 0; i <= k2 || !inserted; ++i) {
+  // a well-formed list ends within n steps; the bound only protects against a corrupted (cyclic) list
+  // restored through rt_env_buffer — a kernel must never spin forever
+  for (int i = 0; (i <= k2 || !inserted) && i <= n + 1; ++i) {
     if (cur != 0 && !have) {
       nd = log[(size_t)(cur - 1) * E];
       have = true;

@@ -38,7 +38,8 @@ def test_bad_config_rejected_before_touching_cuda():
     h = C.c_void_p()
     for bad in (dict(n_envs=0), dict(n_agents=9), dict(grid=1), dict(max_steps=0), dict(max_steps=1, n_agents=1),
                 dict(max_steps=40000, n_agents=2), dict(poly_max=6), dict(poly_min=2, poly_max=1),
-                dict(cell_pitch_cm=0.0), dict(lognorm_step=0)):
+                dict(cell_pitch_cm=0.0), dict(lognorm_step=0), dict(grid=256), dict(src_lo=-1.0),
+                dict(src_lo=5.0, src_hi=1.0), dict(bkg_lo=2.0, bkg_hi=1.0)):
         kw = dict(n_envs=4, n_agents=1, grid=8, max_steps=10, lognorm_step=2, cell_pitch_cm=100.0, min_dist_cm=50.0)
         kw.update(bad)
         c = _lib.EnvCfg(**kw)

@@ -92,7 +92,8 @@ def test_c2_size_single_agent_whole_episode_vs_oracle():
 @pytest.mark.parametrize("kw", [
     dict(n_envs=3, n_agents=2, grid=2, max_steps=5),                       # smallest grid
     dict(n_envs=2, n_agents=8, grid=64, max_steps=8191, poly_min=5, poly_max=5, rect_min=1, rect_max=9),  # T*A = 65,528: near the u16 limit; dense fallback rasteriser? no: 4096 cells
-    dict(n_envs=1, n_agents=1, grid=256, max_steps=30),                    # largest grid: tile too big for smem -> dense path
+    dict(n_envs=2, n_agents=2, grid=248, max_steps=30),                    # 61,504 cells: tile too big for smem -> dense vector path
+    dict(n_envs=1, n_agents=1, grid=255, max_steps=30),                    # largest grid, 65,025 cells -> generic path
     dict(n_envs=5, n_agents=3, grid=13, max_steps=25, poly_min=1, poly_max=3, rect_min=1, rect_max=3),   # 169 cells: generic rasteriser
 ])
 def test_extreme_configurations_vs_oracle(kw):
