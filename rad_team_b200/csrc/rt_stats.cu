@@ -548,7 +548,7 @@ k_est_update(const rt_estimator s, const int32_t* __restrict__ key, const double
   const double v = value[i];
   // sorted insert (after equal values)
   int pred = 0, cur = s.head[i * s.n_keys + k];
-  while (cur != 0 && !(s.value[i * s.capacity + (cur - 1)] > v)) {
+  for (int guard = 0; cur != 0 && !(s.value[i * s.capacity + (cur - 1)] > v) && guard <= idx; ++guard) {
     pred = cur;
     cur = s.next[i * s.capacity + (cur - 1)];
   }
