@@ -110,7 +110,10 @@ typedef enum rt_buf {
   RT_BUF_TICK = 8,       /* int32  [E]      steps since reset              */
   RT_BUF_EPISODE = 9,    /* int32  [E]      resets so far - 1              */
   RT_BUF_VISIT = 10,     /* uint16 [E][G*G] visit counts                   */
-  RT_BUF_INTENSITY = 11, /* float  [E][G*G] normalised intensity map       */
+  RT_BUF_INTENSITY = 11, /* float  [E][G*G] normalised intensity map.  With the default (sparse)
+                            rasteriser the step keeps intensities in VREC only and this dense view
+                            is brought up to date by each rt_env_buffer(INTENSITY) call (which
+                            synchronises the device); with the dense rasterisers it is live */
   RT_BUF_HEAD = 12,      /* uint16 [E][G*G] smallest log entry of the cell + 1 (0 = none) */
   RT_BUF_LOG = 13,       /* uint32 [T*A][E][2] reading log, time-major: {count, next larger
                             entry of the same cell + 1}; entry index = tick*A + agent      */

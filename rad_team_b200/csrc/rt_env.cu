@@ -417,6 +417,7 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
                  { rt_env_destroy(h); });
     }
   }
+  d.live_inten = h->sparse ? 0 : 1;
   RT_CUDA_OR(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking), { rt_env_destroy(h); });
   RT_CUDA_OR(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming), { rt_env_destroy(h); });
   *out = h;
@@ -592,6 +593,14 @@ int rt_env_episode_stats(rt_env* h, double* stats_dev, void* stream) {
 
 int rt_env_buffer(rt_env* h, int which, void** dev_ptr, size_t* bytes) {
   if (!h || which < 0 || which >= RT_BUF__COUNT || !h->buf_ptr[which]) return RT_ERR_BAD_ARG;
+  if (which == RT_BUF_INTENSITY && !h->dev.live_inten) {
+    // sparse mode keeps intensities in the records only: bring the dense view up to date (synchronises)
+    RT_CUDA(cudaDeviceSynchronize());
+    k_densify_intensity<<<(unsigned)((h->dev.E + 127) / 128), 128>>>(h->dev);
+    h->launches += 1;
+    RT_CUDA_LAUNCH_CHECK();
+    RT_CUDA(cudaDeviceSynchronize());
+  }
   if (dev_ptr) *dev_ptr = h->buf_ptr[which];
   if (bytes) *bytes = h->buf_bytes[which];
   return RT_OK;

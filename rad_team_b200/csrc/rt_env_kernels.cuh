@@ -60,6 +60,8 @@ struct EnvDev {
   uint8_t* ep_done;    // [E][A]
   float* rollout;      // [T][E][A] readings sink, or nullptr
   int32_t* step_flags; // one word: OR of the RT_FLAG_* that voided an env's step in the CURRENT launch
+  int live_inten;      // 1: k_step keeps the dense intensity map current (dense / generic rasterisers); 0: the records
+                       //    are the only copy and the dense map is materialised on request (k_densify_intensity)
   uint4* prev_cells;   // [E] the agents' cells BEFORE the last step (8 x uint16), for the incremental observation update
   const double* inj;
   int inj_k;
@@ -207,7 +209,9 @@ __device__ __forceinline__ void stats_chain(const EnvDev& d, const StepSmem& s, 
       fl |= RT_FLAG_NORMALIZE;
       val = 0.0;
     }
-    inten[cell] = (float)val;
+    // one scattered 4-byte store per agent-step is worth ~10 % of this kernel (sensitivity probe):
+    // the sparse rasterisers read the record below, so the dense map is only kept current when something reads it
+    if (d.live_inten) inten[cell] = (float)val;
     rec[2 + sl] = make_uint2((uint32_t)cell | ((uint32_t)n << 16), __float_as_uint((float)val));
     const size_t ia = (size_t)e * A + aa;
     d.last_est[ia] = est;
@@ -951,11 +955,28 @@ k_patch_incremental(const EnvDev d, float* __restrict__ out) {
   for (int a = 0; a < RT_MAX_AGENTS; ++a) {
     const uint32_t c = (curw[a >> 1] >> (16 * (a & 1))) & 0xffffu;
     if (c != 0xffffu) {
-      const size_t m = (size_t)e * d.cells + c;
       o[c] = 1.0f;
-      o[d.cells + c] = d.inten[m];
-      o[2 * (size_t)d.cells + c] = d.lut[d.visit[m]];
+      const int sl = (int)d.slot[(size_t)e * d.cells + c];
+      if (sl != 0) {  // visited this episode (always, after a step; not for a voided env still on its start cell)
+        const uint2 r = rec[2 + sl];  // {cell | visits << 16, fp32 intensity}
+        o[d.cells + c] = __uint_as_float(r.y);
+        o[2 * (size_t)d.cells + c] = d.lut[r.x >> 16];
+      }
     }
+  }
+}
+
+// Materialise the dense intensity map from the records (inspection / state export in sparse mode).
+__global__ void __launch_bounds__(128)
+k_densify_intensity(const EnvDev d) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.E) return;
+  const uint2* rec = d.vrec + (size_t)e * d.rec_stride;
+  float* inten = d.inten + (size_t)e * d.cells;
+  const int nv = (int)rec[0].x;
+  for (int k = 1; k <= nv; ++k) {
+    const uint2 r = rec[2 + k];
+    inten[r.x & 0xffffu] = __uint_as_float(r.y);
   }
 }
 

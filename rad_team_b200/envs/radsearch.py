@@ -157,6 +157,8 @@ class BatchedRadSearchEnv:
         v = self._views.get(name)
         if v is None:
             v = self._views[name] = self._make_view(name)
+        elif name == "INTENSITY":  # materialised from the records on every request (sparse mode)
+            _lib.check(self._L.rt_env_buffer(self._h, _lib.BUF[name], None, None), name)
         return v
 
     def _make_view(self, name: str):
