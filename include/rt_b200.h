@@ -109,12 +109,15 @@ typedef enum rt_buf {
   RT_BUF_EDGES = 7,      /* float  [E][20][4]  (x0,y0,x1,y1) in cell units */
   RT_BUF_TICK = 8,       /* int32  [E]      steps since reset              */
   RT_BUF_EPISODE = 9,    /* int32  [E]      resets so far - 1              */
-  RT_BUF_VISIT = 10,     /* uint16 [E][G*G] visit counts                   */
+  RT_BUF_VISIT = 10,     /* uint16 [E][G*G] visit counts (dense view, see INTENSITY) */
   RT_BUF_INTENSITY = 11, /* float  [E][G*G] normalised intensity map.  With the default (sparse)
-                            rasteriser the step keeps intensities in VREC only and this dense view
-                            is brought up to date by each rt_env_buffer(INTENSITY) call (which
-                            synchronises the device); with the dense rasterisers it is live */
-  RT_BUF_HEAD = 12,      /* uint16 [E][G*G] smallest log entry of the cell + 1 (0 = none) */
+                            rasteriser the step keeps visits and intensities in CELLREC / VREC only
+                            and the dense VISIT / INTENSITY views are brought up to date by each
+                            rt_env_buffer(VISIT or INTENSITY) call (which synchronises the device);
+                            with the dense rasterisers they are live */
+  RT_BUF_CELLREC = 12,   /* uint16 [E][G*G][4] per-cell record of the step kernel: visits, smallest log
+                            entry of the cell + 1 (list head, 0 = none), record index in VREC + 1
+                            (0 = not visited this episode), unused                          */
   RT_BUF_LOG = 13,       /* uint32 [T*A][E][2] reading log, time-major: {count, next larger
                             entry of the same cell + 1}; entry index = tick*A + agent      */
   RT_BUF__RESERVED14 = 14,
@@ -131,7 +134,7 @@ typedef enum rt_buf {
   RT_BUF_VISIT_LUT = 25, /* float  [T*A+1]  BensLogNormalizer table          */
   RT_BUF_EP_RETURN = 26, /* int32  [E][A]   sum of rewards since reset       */
   RT_BUF_EP_DONE = 27,   /* uint8  [E][A]   1 once the agent has reached the source this episode */
-  RT_BUF_SLOT = 28,      /* uint16 [E][G*G] record index of the cell + 1 (0 = not visited this episode) */
+  RT_BUF__RESERVED28 = 28,
   RT_BUF_VREC = 29,      /* uint32 [E][R][2] compact list of visited cells read by the sparse rasteriser:
                             [0] = {n_visited, 0}; [1..2] = agent cells, 8 x uint16 (0xFFFF = none);
                             [2+k] = {cell | visits << 16, fp32 bits of the intensity value};

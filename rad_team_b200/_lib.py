@@ -18,9 +18,9 @@ MAX_AGENTS, MAX_POLYS, MAX_EDGES = 8, 5, 20
 
 BUF = dict(
     AGENT_XY=0, PREV_DIST=1, START_XY=2, SRC_XY=3, SRC_INT=4, BKG=5, N_POLY=6, EDGES=7, TICK=8, EPISODE=9,
-    VISIT=10, INTENSITY=11, HEAD=12, LOG=13, WELFORD=15, WELFORD_N=16, EST_MAXMIN=17, FLAGS=18,
+    VISIT=10, INTENSITY=11, CELLREC=12, LOG=13, WELFORD=15, WELFORD_N=16, EST_MAXMIN=17, FLAGS=18,
     LAST_COUNT=19, LAST_LOS=20, LAST_LAMBDA=21, LAST_EST=22, LAST_Z=23, LAST_VALUE=24, VISIT_LUT=25,
-    EP_RETURN=26, EP_DONE=27, SLOT=28, VREC=29,
+    EP_RETURN=26, EP_DONE=27, VREC=29,
 )
 
 

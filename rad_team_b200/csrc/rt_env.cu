@@ -270,11 +270,11 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
       /*AGENT_XY*/ E * A * 8,   /*PREV_DIST*/ E * A * 4, /*START_XY*/ E * A * 8, /*SRC_XY*/ E * 8,
       /*SRC_INT*/ E * 8,        /*BKG*/ E * 8,           /*N_POLY*/ E * 4,       /*EDGES*/ E * RT_MAX_EDGES * 16,
       /*TICK*/ E * 4,           /*EPISODE*/ E * 4,       /*VISIT*/ E * cells * 2, /*INTENSITY*/ E * cells * 4,
-      /*HEAD*/ E * cells * 2,   /*LOG*/ (size_t)cap * E * 8, /*unused*/ 0,       /*WELFORD*/ E * 48,
+      /*CELLREC*/ E * cells * 8,   /*LOG*/ (size_t)cap * E * 8, /*unused*/ 0,       /*WELFORD*/ E * 48,
       /*WELFORD_N*/ E * 4,      /*EST_MAXMIN*/ E * 16,   /*FLAGS*/ E * 4,        /*LAST_COUNT*/ E * A * 4,
       /*LAST_LOS*/ E * A,       /*LAST_LAMBDA*/ E * A * 8, /*LAST_EST*/ E * A * 8, /*LAST_Z*/ E * A * 8,
       /*LAST_VALUE*/ E * A * 8, /*VISIT_LUT*/ ((size_t)cap + 1) * 4, /*EP_RETURN*/ E * A * 4,
-      /*EP_DONE*/ E * A,        /*SLOT*/ E * cells * 2,  /*VREC*/ E * (size_t)rec_stride * 8};
+      /*EP_DONE*/ E * A,        /*reserved*/ 0,  /*VREC*/ E * (size_t)rec_stride * 8};
   Carver cv;
   size_t off[RT_BUF__COUNT];
   for (int i = 0; i < RT_BUF__COUNT; ++i) off[i] = cv.take(sz[i]);
@@ -327,7 +327,7 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
   d.episode = (int32_t*)h->buf_ptr[RT_BUF_EPISODE];
   d.visit = (uint16_t*)h->buf_ptr[RT_BUF_VISIT];
   d.inten = (float*)h->buf_ptr[RT_BUF_INTENSITY];
-  d.head = (uint16_t*)h->buf_ptr[RT_BUF_HEAD];
+  d.cellrec = (uint16_t*)h->buf_ptr[RT_BUF_CELLREC];
   d.log = (uint2*)h->buf_ptr[RT_BUF_LOG];
   d.welford = (double*)h->buf_ptr[RT_BUF_WELFORD];
   d.welford_n = (int32_t*)h->buf_ptr[RT_BUF_WELFORD_N];
@@ -342,7 +342,6 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
   d.lut = (float*)h->buf_ptr[RT_BUF_VISIT_LUT];
   d.ep_return = (int32_t*)h->buf_ptr[RT_BUF_EP_RETURN];
   d.ep_done = (uint8_t*)h->buf_ptr[RT_BUF_EP_DONE];
-  d.slot = (uint16_t*)h->buf_ptr[RT_BUF_SLOT];
   d.vrec = (uint2*)h->buf_ptr[RT_BUF_VREC];
   d.rec_stride = rec_stride;
   d.rec_prefix = rec_stride < 128 ? rec_stride : 128;  // 1 KB per env covers 125 visited cells; the rest is read directly
@@ -417,7 +416,7 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
                  { rt_env_destroy(h); });
     }
   }
-  d.live_inten = h->sparse ? 0 : 1;
+  d.live_dense = h->sparse ? 0 : 1;
   RT_CUDA_OR(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking), { rt_env_destroy(h); });
   RT_CUDA_OR(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming), { rt_env_destroy(h); });
   *out = h;
@@ -593,10 +592,10 @@ int rt_env_episode_stats(rt_env* h, double* stats_dev, void* stream) {
 
 int rt_env_buffer(rt_env* h, int which, void** dev_ptr, size_t* bytes) {
   if (!h || which < 0 || which >= RT_BUF__COUNT || !h->buf_ptr[which]) return RT_ERR_BAD_ARG;
-  if (which == RT_BUF_INTENSITY && !h->dev.live_inten) {
-    // sparse mode keeps intensities in the records only: bring the dense view up to date (synchronises)
+  if ((which == RT_BUF_INTENSITY || which == RT_BUF_VISIT) && !h->dev.live_dense) {
+    // sparse mode keeps visits / intensities in the records only: bring the dense views up to date (synchronises)
     RT_CUDA(cudaDeviceSynchronize());
-    k_densify_intensity<<<(unsigned)((h->dev.E + 127) / 128), 128>>>(h->dev);
+    k_densify<<<(unsigned)((h->dev.E + 127) / 128), 128>>>(h->dev);
     h->launches += 1;
     RT_CUDA_LAUNCH_CHECK();
     RT_CUDA(cudaDeviceSynchronize());

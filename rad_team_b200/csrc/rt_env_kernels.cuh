@@ -35,10 +35,11 @@ struct EnvDev {
   float* edges;  // [E][20][4]
   int32_t* tick;
   int32_t* episode;
-  uint16_t* visit;  // [E][cells]
-  float* inten;     // [E][cells]
-  uint16_t* head;   // [E][cells]  smallest log entry of the cell, +1 (0 = empty)
-  uint16_t* slot;   // [E][cells]  record index of the cell in vrec, +1 (0 = never visited this episode)
+  uint16_t* visit;  // [E][cells]  dense visit counts: live only when live_dense, else materialised on request
+  float* inten;     // [E][cells]  dense intensity map: likewise
+  uint16_t* cellrec;  // [E][cells][4]  k_step's random-access state of a cell, ONE 8-byte record per cell so that a
+                      //   visit costs one DRAM sector instead of three: [0] visits, [1] smallest log entry of the
+                      //   cell + 1 (list head, 0 = empty), [2] record index in vrec + 1 (0 = not visited), [3] unused
   uint2* vrec;      // [E][rec_stride]  compact list of the VISITED cells, what the sparse rasteriser reads:
                     //   [0] = {n_visited, 0}; [1..2] = the agents' cells, 8 x uint16 (0xFFFF = none);
                     //   [2 + k] = {cell | visits << 16, fp32 bits of the intensity value}, k = 1..n_visited
@@ -60,8 +61,8 @@ struct EnvDev {
   uint8_t* ep_done;    // [E][A]
   float* rollout;      // [T][E][A] readings sink, or nullptr
   int32_t* step_flags; // one word: OR of the RT_FLAG_* that voided an env's step in the CURRENT launch
-  int live_inten;      // 1: k_step keeps the dense intensity map current (dense / generic rasterisers); 0: the records
-                       //    are the only copy and the dense map is materialised on request (k_densify_intensity)
+  int live_dense;      // 1: k_step keeps the dense visit / intensity maps current (dense / generic rasterisers); 0: cell
+                       //    records + visited-cell records are the only copy, dense maps are materialised on request
   uint4* prev_cells;   // [E] the agents' cells BEFORE the last step (8 x uint16), for the incremental observation update
   const double* inj;
   int inj_k;
@@ -175,9 +176,8 @@ __device__ __forceinline__ double list_insert_median(uint2* __restrict__ log, si
 __device__ __forceinline__ void stats_chain(const EnvDev& d, const StepSmem& s, int e, int le, int tick,
                                             WelfordState& w, double emx, double emn, int nv) {
   const int A = d.A;
+  uint16_t* crec = d.cellrec + (size_t)e * d.cells * 4;
   uint16_t* visit = d.visit + (size_t)e * d.cells;
-  uint16_t* head = d.head + (size_t)e * d.cells;
-  uint16_t* slot = d.slot + (size_t)e * d.cells;
   uint2* rec = d.vrec + (size_t)e * d.rec_stride;
   float* inten = d.inten + (size_t)e * d.cells;
   int fl = s.eflags[le];
@@ -190,15 +190,17 @@ __device__ __forceinline__ void stats_chain(const EnvDev& d, const StepSmem& s, 
       est = s.est[i];
       sl = s.slot[i];
     } else {
-      n = (int)visit[cell] + 1;
-      visit[cell] = (uint16_t)n;
-      est = list_insert_median(d.log + e, (size_t)d.E, head + cell, tick * A + aa, s.count[i], n, (int)head[cell],
-                               make_uint2(0u, 0u), false);
-      sl = (int)slot[cell];
+      const uint2 cr = *reinterpret_cast<const uint2*>(crec + 4 * cell);
+      n = (int)(cr.x & 0xffffu) + 1;
+      crec[4 * cell] = (uint16_t)n;
+      if (d.live_dense) visit[cell] = (uint16_t)n;
+      est = list_insert_median(d.log + e, (size_t)d.E, crec + 4 * cell + 1, tick * A + aa, s.count[i], n,
+                               (int)(cr.x >> 16), make_uint2(0u, 0u), false);
+      sl = (int)(cr.y & 0xffffu);
     }
     if (sl == 0) {  // first visit of this cell in the episode: open a record
       sl = ++nv;
-      slot[cell] = (uint16_t)sl;
+      crec[4 * cell + 2] = (uint16_t)sl;
     }
     est_maxmin(est, emx, emn);
 
@@ -211,7 +213,7 @@ __device__ __forceinline__ void stats_chain(const EnvDev& d, const StepSmem& s, 
     }
     // one scattered 4-byte store per agent-step is worth ~10 % of this kernel (sensitivity probe):
     // the sparse rasterisers read the record below, so the dense map is only kept current when something reads it
-    if (d.live_inten) inten[cell] = (float)val;
+    if (d.live_dense) inten[cell] = (float)val;
     rec[2 + sl] = make_uint2((uint32_t)cell | ((uint32_t)n << 16), __float_as_uint((float)val));
     const size_t ia = (size_t)e * A + aa;
     d.last_est[ia] = est;
@@ -372,9 +374,10 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
     s.cell[t] = cell;
     if (live) {  // cell state for the estimator: the loads fly while line of sight and sampler compute
       const size_t mcell = (size_t)e * d.cells + cell;
-      pv = d.visit[mcell];
-      ph = d.head[mcell];
-      psl = d.slot[mcell];
+      const uint2 cr = reinterpret_cast<const uint2*>(d.cellrec)[mcell];  // visits | head << 16, slot
+      pv = cr.x & 0xffffu;
+      ph = cr.x >> 16;
+      psl = cr.y & 0xffffu;
     }
   }
   __syncthreads();  // every agent's new cell is known to its env-mates
@@ -413,8 +416,10 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
     double est = 0.0;
     if (!clash) {
       n = (int)pv + 1;
-      d.visit[(size_t)e * d.cells + cell] = (uint16_t)n;
-      est = list_insert_median(d.log + e, (size_t)d.E, d.head + (size_t)e * d.cells + cell, tick * A + a, (int)cnt,
+      uint16_t* cr16 = d.cellrec + ((size_t)e * d.cells + cell) * 4;
+      cr16[0] = (uint16_t)n;
+      if (d.live_dense) d.visit[(size_t)e * d.cells + cell] = (uint16_t)n;
+      est = list_insert_median(d.log + e, (size_t)d.E, cr16 + 1, tick * A + a, (int)cnt,
                                n, (int)ph, pnode, ph != 0u);
     }
     s.count[t] = (int)cnt;
@@ -563,29 +568,27 @@ k_reset_state(const EnvDev d, const uint8_t* __restrict__ mask, int32_t* __restr
   reinterpret_cast<double2*>(d.est_mm)[e] = make_double2(0.0, 0.0);  // estimator.py:25-29
 }
 
-// visit (2 B) + head (2 B) + slot (2 B) + intensity (4 B) per cell; 16-byte stores, one CTA per env.
+// cell records (8 B) + dense visit (2 B) + dense intensity (4 B) per cell; 16-byte stores, one CTA per env.
 __global__ void __launch_bounds__(256)
 k_zero_maps(const EnvDev d, const uint8_t* __restrict__ mask) {
   const int e = blockIdx.x;
   if (mask != nullptr && mask[e] == 0) return;
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-  const size_t b16 = (size_t)d.cells * 2, b32 = (size_t)d.cells * 4;
+  const size_t b16 = (size_t)d.cells * 2, b32 = (size_t)d.cells * 4, b64 = (size_t)d.cells * 8;
   unsigned char* v = reinterpret_cast<unsigned char*>(d.visit) + (size_t)e * b16;
-  unsigned char* h = reinterpret_cast<unsigned char*>(d.head) + (size_t)e * b16;
-  unsigned char* sl = reinterpret_cast<unsigned char*>(d.slot) + (size_t)e * b16;
+  unsigned char* c = reinterpret_cast<unsigned char*>(d.cellrec) + (size_t)e * b64;
   unsigned char* f = reinterpret_cast<unsigned char*>(d.inten) + (size_t)e * b32;
+  if ((d.cells & 1) == 0) {  // an env's cell records start 16-byte aligned only when cells is even
+    for (size_t i = threadIdx.x * 16; i < b64; i += blockDim.x * 16) *reinterpret_cast<uint4*>(c + i) = z;
+  } else {
+    for (size_t i = threadIdx.x * 8; i < b64; i += blockDim.x * 8) *reinterpret_cast<uint2*>(c + i) = make_uint2(0u, 0u);
+  }
   if ((d.cells & 7) == 0) {
-    for (size_t i = threadIdx.x * 16; i < b16; i += blockDim.x * 16) {
-      *reinterpret_cast<uint4*>(v + i) = z;
-      *reinterpret_cast<uint4*>(h + i) = z;
-      *reinterpret_cast<uint4*>(sl + i) = z;
-    }
+    for (size_t i = threadIdx.x * 16; i < b16; i += blockDim.x * 16) *reinterpret_cast<uint4*>(v + i) = z;
     for (size_t i = threadIdx.x * 16; i < b32; i += blockDim.x * 16) *reinterpret_cast<uint4*>(f + i) = z;
   } else {
     for (int i = threadIdx.x; i < d.cells; i += blockDim.x) {
       d.visit[(size_t)e * d.cells + i] = 0;
-      d.head[(size_t)e * d.cells + i] = 0;
-      d.slot[(size_t)e * d.cells + i] = 0;
       d.inten[(size_t)e * d.cells + i] = 0.f;
     }
   }
@@ -956,7 +959,7 @@ k_patch_incremental(const EnvDev d, float* __restrict__ out) {
     const uint32_t c = (curw[a >> 1] >> (16 * (a & 1))) & 0xffffu;
     if (c != 0xffffu) {
       o[c] = 1.0f;
-      const int sl = (int)d.slot[(size_t)e * d.cells + c];
+      const int sl = (int)d.cellrec[((size_t)e * d.cells + c) * 4 + 2];
       if (sl != 0) {  // visited this episode (always, after a step; not for a voided env still on its start cell)
         const uint2 r = rec[2 + sl];  // {cell | visits << 16, fp32 intensity}
         o[d.cells + c] = __uint_as_float(r.y);
@@ -966,17 +969,19 @@ k_patch_incremental(const EnvDev d, float* __restrict__ out) {
   }
 }
 
-// Materialise the dense intensity map from the records (inspection / state export in sparse mode).
+// Materialise the dense visit / intensity maps from the records (inspection / state export in sparse mode).
 __global__ void __launch_bounds__(128)
-k_densify_intensity(const EnvDev d) {
+k_densify(const EnvDev d) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.E) return;
   const uint2* rec = d.vrec + (size_t)e * d.rec_stride;
   float* inten = d.inten + (size_t)e * d.cells;
+  uint16_t* visit = d.visit + (size_t)e * d.cells;
   const int nv = (int)rec[0].x;
   for (int k = 1; k <= nv; ++k) {
     const uint2 r = rec[2 + k];
     inten[r.x & 0xffffu] = __uint_as_float(r.y);
+    visit[r.x & 0xffffu] = (uint16_t)(r.x >> 16);
   }
 }
 

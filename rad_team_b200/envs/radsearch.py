@@ -63,7 +63,7 @@ _BUF_SPEC = {
     "EPISODE": ("int32", lambda E, A, c, cap: (E,)),
     "VISIT": ("uint16", lambda E, A, c, cap: (E, c)),
     "INTENSITY": ("float32", lambda E, A, c, cap: (E, c)),
-    "HEAD": ("uint16", lambda E, A, c, cap: (E, c)),
+    "CELLREC": ("uint16", lambda E, A, c, cap: (E, c, 4)),
     "LOG": ("int32", lambda E, A, c, cap: (cap, E, 2)),
     "WELFORD": ("float64", lambda E, A, c, cap: (E, 6)),
     "WELFORD_N": ("int32", lambda E, A, c, cap: (E,)),
@@ -78,7 +78,6 @@ _BUF_SPEC = {
     "VISIT_LUT": ("float32", lambda E, A, c, cap: (cap + 1,)),
     "EP_RETURN": ("int32", lambda E, A, c, cap: (E, A)),
     "EP_DONE": ("uint8", lambda E, A, c, cap: (E, A)),
-    "SLOT": ("uint16", lambda E, A, c, cap: (E, c)),
     "VREC": ("int32", lambda E, A, c, cap: (E, (3 + min(cap, c) + 1) & ~1, 2)),
 }
 _ITEMSIZE = {"int32": 4, "float64": 8, "float32": 4, "uint16": 2, "uint8": 1}
@@ -157,7 +156,7 @@ class BatchedRadSearchEnv:
         v = self._views.get(name)
         if v is None:
             v = self._views[name] = self._make_view(name)
-        elif name == "INTENSITY":  # materialised from the records on every request (sparse mode)
+        elif name in ("INTENSITY", "VISIT"):  # materialised from the records on every request (sparse mode)
             _lib.check(self._L.rt_env_buffer(self._h, _lib.BUF[name], None, None), name)
         return v
 

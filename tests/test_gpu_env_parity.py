@@ -314,7 +314,7 @@ def test_sparse_and_dense_rasterisers_agree(monkeypatch, kw):
         assert torch.equal(sparse.obs_maps, split.obs_maps), t
         assert torch.equal(sparse.obs_maps, tma.obs_maps), t
         assert np.array_equal(sparse.obs_maps.cpu().numpy(), m_o), t
-    for k in ("VISIT", "INTENSITY", "WELFORD", "LOG", "HEAD", "SLOT", "VREC"):
+    for k in ("VISIT", "INTENSITY", "WELFORD", "LOG", "CELLREC", "VREC"):
         assert torch.equal(sparse.buffer(k), dense.buffer(k)), k
     nv = sparse.buffer("VREC")[:, 0, 0].cpu().numpy()
     assert np.array_equal(nv, (sparse.buffer("VISIT").cpu().numpy() > 0).sum(1))
