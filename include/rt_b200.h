@@ -14,6 +14,10 @@
  *   - pointers suffixed _dev are DEVICE pointers owned by the caller (PyTorch
  *     tensors), _host are HOST pointers; the handle owns all persistent state;
  *   - nothing here synchronises the device unless its comment says so;
+ *   - a handle belongs to the CUDA device that was current in rt_*_create; its
+ *     other entry points run on that device whatever the calling thread has
+ *     selected since (and restore the caller's selection).  A handle is not
+ *     thread-safe: one caller, one stream at a time;
  *   - there is no CPU fallback: without a CUDA device every compute entry
  *     point returns RT_ERR_CUDA.
  *

@@ -131,6 +131,12 @@ def check(rc: int, what: str = "") -> None:
     raise RtError(msg)
 
 
+def require(cond: bool, what: str) -> None:
+    """Argument validation in front of raw-pointer calls: a real exception, not an `assert` (python -O keeps it)."""
+    if not cond:
+        raise ValueError(what)
+
+
 def require_cuda():
     """The product has no CPU path: fail loudly when there is no device."""
     import torch

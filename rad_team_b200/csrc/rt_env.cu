@@ -425,6 +425,7 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
 
 int rt_env_destroy(rt_env* h) {
   if (!h) return RT_OK;
+  RtDeviceGuard on_device(h->device);
   if (h->aux) {
     cudaStreamSynchronize(h->aux);
     cudaStreamDestroy(h->aux);
@@ -439,6 +440,7 @@ int rt_env_destroy(rt_env* h) {
 int rt_env_set_scenario(rt_env* h, const int32_t* src_xy, const double* src_int, const double* bkg,
                         const int32_t* start_xy, const int32_t* n_poly, const float* edges) {
   if (!h) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(h->device);
   const size_t E = (size_t)h->dev.E, A = (size_t)h->dev.A;
   if (src_xy)
     for (size_t i = 0; i < E * 2; ++i)
@@ -461,12 +463,14 @@ int rt_env_set_scenario(rt_env* h, const int32_t* src_xy, const double* src_int,
 int rt_env_reset(rt_env* h, const uint8_t* mask_dev, int32_t* obs_xy_dev, float* obs_maps_dev,
                  void* stream) {
   if (!h) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(h->device);
   return launch_reset(h, mask_dev, obs_xy_dev, obs_maps_dev, (cudaStream_t)stream);
 }
 
 int rt_env_step(rt_env* h, const int32_t* actions_dev, int32_t* obs_xy_dev, float* obs_maps_dev,
                 int32_t* reward_dev, uint8_t* done_dev, void* stream) {
   if (!h || !actions_dev || !obs_xy_dev || !reward_dev || !done_dev) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(h->device);
   return launch_step(h, actions_dev, obs_xy_dev, obs_maps_dev, reward_dev, done_dev,
                      (cudaStream_t)stream);
 }
@@ -474,6 +478,7 @@ int rt_env_step(rt_env* h, const int32_t* actions_dev, int32_t* obs_xy_dev, floa
 int rt_env_reset_host(rt_env* h, const uint8_t* mask_host, int32_t* obs_xy_host, float* obs_maps_dev,
                       void* stream) {
   if (!h) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t E = (size_t)h->dev.E, A = (size_t)h->dev.A;
   const uint8_t* mask_dev = nullptr;
@@ -484,7 +489,7 @@ int rt_env_reset_host(rt_env* h, const uint8_t* mask_host, int32_t* obs_xy_host,
       std::memcpy(pm, mask_host, E);
       srcp = pm;
     }
-    RT_CUDA(cudaMemcpyAsync(h->d_mask, srcp, E, cudaMemcpyHostToDevice, st));
+    RT_CUDA(cudaMemcpyAsync(h->d_mask, srcp, E, cudaMemcpyDefault, st));
     mask_dev = h->d_mask;
   }
   const int rc = launch_reset(h, mask_dev, h->d_obs_xy, obs_maps_dev, st);
@@ -492,7 +497,7 @@ int rt_env_reset_host(rt_env* h, const uint8_t* mask_host, int32_t* obs_xy_host,
   if (obs_xy_host) {
     const bool direct = is_pinned_or_device(obs_xy_host);
     void* dst = direct ? (void*)obs_xy_host : (void*)(h->pinned + E * A * 4);
-    RT_CUDA(cudaMemcpyAsync(dst, h->d_obs_xy, E * A * 8, cudaMemcpyDeviceToHost, st));
+    RT_CUDA(cudaMemcpyAsync(dst, h->d_obs_xy, E * A * 8, cudaMemcpyDefault, st));
     RT_CUDA(cudaStreamSynchronize(st));
     if (!direct) std::memcpy(obs_xy_host, dst, E * A * 8);
   } else {
@@ -504,6 +509,7 @@ int rt_env_reset_host(rt_env* h, const uint8_t* mask_host, int32_t* obs_xy_host,
 int rt_env_step_host(rt_env* h, const int32_t* actions_host, int32_t* obs_xy_host, int32_t* reward_host,
                      uint8_t* done_host, float* obs_maps_dev, void* stream) {
   if (!h || !actions_host || !obs_xy_host || !reward_host || !done_host) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = (size_t)h->dev.E * h->dev.A;
   unsigned char* p_act = h->pinned;
@@ -524,7 +530,7 @@ int rt_env_step_host(rt_env* h, const int32_t* actions_host, int32_t* obs_xy_hos
       std::memcpy(p_act, actions_host, n * 4);
       a_src = p_act;
     }
-    RT_CUDA(cudaMemcpyAsync(h->d_actions, a_src, n * 4, cudaMemcpyHostToDevice, st));
+    RT_CUDA(cudaMemcpyAsync(h->d_actions, a_src, n * 4, cudaMemcpyDefault, st));
   }
   RT_CUDA(cudaMemsetAsync(h->dev.step_flags, 0, 4, st));
   // k_step, then the small results travel back on the auxiliary stream WHILE the rasteriser streams
@@ -534,9 +540,9 @@ int rt_env_step_host(rt_env* h, const int32_t* actions_host, int32_t* obs_xy_hos
   RT_CUDA(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
   const bool dx = is_pinned_or_device(obs_xy_host), dr = is_pinned_or_device(reward_host),
              dd = is_pinned_or_device(done_host);
-  RT_CUDA(cudaMemcpyAsync(dx ? (void*)obs_xy_host : (void*)p_xy, h->d_obs_xy, n * 8, cudaMemcpyDeviceToHost, h->aux));
-  RT_CUDA(cudaMemcpyAsync(dr ? (void*)reward_host : (void*)p_rw, h->d_reward, n * 4, cudaMemcpyDeviceToHost, h->aux));
-  RT_CUDA(cudaMemcpyAsync(dd ? (void*)done_host : (void*)p_dn, h->d_done, n, cudaMemcpyDeviceToHost, h->aux));
+  RT_CUDA(cudaMemcpyAsync(dx ? (void*)obs_xy_host : (void*)p_xy, h->d_obs_xy, n * 8, cudaMemcpyDefault, h->aux));
+  RT_CUDA(cudaMemcpyAsync(dr ? (void*)reward_host : (void*)p_rw, h->d_reward, n * 4, cudaMemcpyDefault, h->aux));
+  RT_CUDA(cudaMemcpyAsync(dd ? (void*)done_host : (void*)p_dn, h->d_done, n, cudaMemcpyDefault, h->aux));
   int32_t* p_fl = reinterpret_cast<int32_t*>(h->pinned + h->pinned_bytes - 16);
   RT_CUDA(cudaMemcpyAsync(p_fl, h->dev.step_flags, 4, cudaMemcpyDeviceToHost, h->aux));
   if (obs_maps_dev) {
@@ -554,6 +560,7 @@ int rt_env_step_host(rt_env* h, const int32_t* actions_host, int32_t* obs_xy_hos
 
 int rt_env_rasterize(rt_env* h, float* obs_maps_dev, void* stream) {
   if (!h || !obs_maps_dev) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(h->device);
   return launch_raster(h, obs_maps_dev, (cudaStream_t)stream);
 }
 
@@ -579,6 +586,7 @@ int rt_env_set_rollout(rt_env* h, float* readings_dev) {
 
 int rt_env_episode_stats(rt_env* h, double* stats_dev, void* stream) {
   if (!h || !stats_dev) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   RT_CUDA(cudaMemsetAsync(stats_dev, 0, 3 * sizeof(double), st));
   long long blocks = ((long long)h->dev.E * h->dev.A + 255) / 256;
@@ -592,6 +600,7 @@ int rt_env_episode_stats(rt_env* h, double* stats_dev, void* stream) {
 
 int rt_env_buffer(rt_env* h, int which, void** dev_ptr, size_t* bytes) {
   if (!h || which < 0 || which >= RT_BUF__COUNT || !h->buf_ptr[which]) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(h->device);
   if ((which == RT_BUF_INTENSITY || which == RT_BUF_VISIT) && !h->dev.live_dense) {
     // sparse mode keeps visits / intensities in the records only: bring the dense views up to date (synchronises)
     RT_CUDA(cudaDeviceSynchronize());
@@ -607,6 +616,7 @@ int rt_env_buffer(rt_env* h, int which, void** dev_ptr, size_t* bytes) {
 
 int rt_env_errors(rt_env* h, int32_t* flags_host, void* stream) {
   if (!h || !flags_host) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   RT_CUDA(cudaMemsetAsync(h->d_flag_or, 0, 4, st));
   int blocks = (h->dev.E + 255) / 256;

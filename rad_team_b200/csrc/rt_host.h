@@ -8,6 +8,21 @@
 const char* rt_last_cuda_error();
 void rt_note_cuda_error(cudaError_t err, const char* what);
 
+// A handle belongs to the device that was current when it was created; its entry points run there
+// whatever device the calling thread has selected since, and restore the caller's choice on return.
+struct RtDeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit RtDeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~RtDeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  RtDeviceGuard(const RtDeviceGuard&) = delete;
+  RtDeviceGuard& operator=(const RtDeviceGuard&) = delete;
+};
+
 #define RT_CUDA(call)                         \
   do {                                        \
     cudaError_t rt_e_ = (call);               \

@@ -17,6 +17,7 @@ using namespace rt;
 // ============================================================================================
 // Per-stream Welford: state double[n][6] = mean, M2, var, std, zmax, zmin; int32[n] count.
 struct rt_welford {
+  int device = 0;
   long long n = 0;
   double* state = nullptr;
   int32_t* count = nullptr;
@@ -95,6 +96,7 @@ int rt_welford_create(int64_t n, rt_welford** out) {
   rt_welford* w = new (std::nothrow) rt_welford();
   if (!w) return RT_ERR_NOMEM;
   w->n = n;
+  cudaGetDevice(&w->device);
   if (cudaMalloc((void**)&w->state, (size_t)n * 48) != cudaSuccess ||
       cudaMalloc((void**)&w->count, (size_t)n * 4) != cudaSuccess) {
     rt_note_cuda_error(cudaGetLastError(), "cudaMalloc(welford)");
@@ -106,13 +108,14 @@ int rt_welford_create(int64_t n, rt_welford** out) {
     rt_welford_destroy(w);
     return rc;
   }
-  RT_CUDA(cudaDeviceSynchronize());
+  RT_CUDA_OR(cudaDeviceSynchronize(), { rt_welford_destroy(w); });
   *out = w;
   return RT_OK;
 }
 
 int rt_welford_destroy(rt_welford* w) {
   if (!w) return RT_OK;
+  RtDeviceGuard on_device(w->device);
   if (w->state) cudaFree(w->state);
   if (w->count) cudaFree(w->count);
   delete w;
@@ -121,6 +124,7 @@ int rt_welford_destroy(rt_welford* w) {
 
 int rt_welford_reset(rt_welford* w, void* stream) {
   if (!w) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(w->device);
   k_welford_reset<<<(unsigned)((w->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w->state, w->count, w->n);
   RT_CUDA_LAUNCH_CHECK();
   return RT_OK;
@@ -128,6 +132,7 @@ int rt_welford_reset(rt_welford* w, void* stream) {
 
 int rt_welford_update(rt_welford* w, const double* reading_dev, int32_t* err_dev, void* stream) {
   if (!w || !reading_dev) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(w->device);
   k_welford_update<<<(unsigned)((w->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       w->state, w->count, reading_dev, err_dev, w->n);
   RT_CUDA_LAUNCH_CHECK();
@@ -137,6 +142,7 @@ int rt_welford_update(rt_welford* w, const double* reading_dev, int32_t* err_dev
 int rt_welford_standardize(rt_welford* w, const double* reading_dev, double* z_dev, int32_t* err_dev,
                            void* stream) {
   if (!w || !reading_dev || !z_dev) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(w->device);
   k_welford_standardize<<<(unsigned)((w->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       w->state, reading_dev, z_dev, err_dev, w->n);
   RT_CUDA_LAUNCH_CHECK();
@@ -145,6 +151,7 @@ int rt_welford_standardize(rt_welford* w, const double* reading_dev, double* z_d
 
 int rt_welford_buffers(rt_welford* w, void** state_dev, void** count_dev) {
   if (!w) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(w->device);
   if (state_dev) *state_dev = w->state;
   if (count_dev) *count_dev = w->count;
   return RT_OK;
@@ -163,6 +170,7 @@ int rt_welford_buffers(rt_welford* w, void** state_dev, void** count_dev) {
 // folds the result into the running state.  Every merge order is fixed by (n, grid), so the result
 // is deterministic run to run; it differs from the sequential recurrence only by rounding.
 struct rt_moments {
+  int device = 0;
   double* state = nullptr;     // [3]
   double* partials = nullptr;  // [max_blocks][3]
   int max_blocks = 0;
@@ -367,9 +375,9 @@ int rt_moments_create(rt_moments** out) {
   }
   rt_moments* m = new (std::nothrow) rt_moments();
   if (!m) return RT_ERR_NOMEM;
-  int dev = 0, n_sm = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  int n_sm = 148;
+  cudaGetDevice(&m->device);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, m->device);
   m->max_blocks = n_sm * 8;  // 8 resident 256-thread CTAs per SM: one full wave
   if (cudaMalloc((void**)&m->state, 3 * sizeof(double)) != cudaSuccess ||
       cudaMalloc((void**)&m->partials, (size_t)m->max_blocks * 3 * sizeof(double)) != cudaSuccess) {
@@ -377,13 +385,14 @@ int rt_moments_create(rt_moments** out) {
     rt_moments_destroy(m);
     return RT_ERR_NOMEM;
   }
-  RT_CUDA(cudaMemset(m->state, 0, 3 * sizeof(double)));
+  RT_CUDA_OR(cudaMemset(m->state, 0, 3 * sizeof(double)), { rt_moments_destroy(m); });
   *out = m;
   return RT_OK;
 }
 
 int rt_moments_destroy(rt_moments* m) {
   if (!m) return RT_OK;
+  RtDeviceGuard on_device(m->device);
   if (m->state) cudaFree(m->state);
   if (m->partials) cudaFree(m->partials);
   delete m;
@@ -392,12 +401,14 @@ int rt_moments_destroy(rt_moments* m) {
 
 int rt_moments_reset(rt_moments* m, void* stream) {
   if (!m) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(m->device);
   RT_CUDA(cudaMemsetAsync(m->state, 0, 3 * sizeof(double), (cudaStream_t)stream));
   return RT_OK;
 }
 
 int rt_moments_update(rt_moments* m, const float* x_dev, int64_t n, void* stream) {
   if (!m || !x_dev || n < 0) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(m->device);
   if (((uintptr_t)x_dev & 15) != 0) return RT_ERR_BAD_ARG;  // 16-byte vector loads
   if (n == 0) return RT_OK;
   long long blocks = ((n >> 2) + kMomThreads * kMomUnroll - 1) / (kMomThreads * kMomUnroll);
@@ -411,6 +422,7 @@ int rt_moments_update(rt_moments* m, const float* x_dev, int64_t n, void* stream
 
 int rt_moments_standardize(rt_moments* m, const float* x_dev, float* out_dev, int64_t n, void* stream) {
   if (!m || !x_dev || !out_dev || n < 0) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(m->device);
   if ((((uintptr_t)x_dev | (uintptr_t)out_dev) & 15) != 0) return RT_ERR_BAD_ARG;
   if (n == 0) return RT_OK;
   long long blocks = ((n >> 2) + 255) / 256;
@@ -423,6 +435,7 @@ int rt_moments_standardize(rt_moments* m, const float* x_dev, float* out_dev, in
 
 int rt_moments_state(rt_moments* m, void** state_dev) {
   if (!m || !state_dev) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(m->device);
   *state_dev = m->state;
   return RT_OK;
 }
@@ -430,6 +443,7 @@ int rt_moments_state(rt_moments* m, void** state_dev) {
 int rt_moments_merge(rt_moments* m, const double* gathered_dev, int32_t n_ranks, int32_t stride_doubles,
                      void* stream) {
   if (!m || !gathered_dev || n_ranks < 1 || stride_doubles < 3) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(m->device);
   k_moments_merge<<<1, 32, 0, (cudaStream_t)stream>>>(gathered_dev, n_ranks, stride_doubles, m->state);
   RT_CUDA_LAUNCH_CHECK();
   return RT_OK;
@@ -507,6 +521,7 @@ int rt_lognormalize(const double* current_dev, double max, int32_t step_size, do
 // sorted by value (median = walk to the middle), and the node array itself is insertion order
 // (get_buffer = filtered scan).
 struct rt_estimator {
+  int device = 0;
   long long n = 0;
   int n_keys = 0, capacity = 0;
   double* value = nullptr;   // [n][capacity]
@@ -623,6 +638,7 @@ int rt_estimator_create(int64_t n, int32_t n_keys, int32_t capacity, rt_estimato
   s->n = n;
   s->n_keys = n_keys;
   s->capacity = capacity;
+  cudaGetDevice(&s->device);
   const size_t nc = (size_t)n * capacity, nk = (size_t)n * n_keys;
   bool ok = cudaMalloc((void**)&s->value, nc * 8) == cudaSuccess &&
             cudaMalloc((void**)&s->key, nc * 4) == cudaSuccess &&
@@ -641,13 +657,14 @@ int rt_estimator_create(int64_t n, int32_t n_keys, int32_t capacity, rt_estimato
     rt_estimator_destroy(s);
     return rc;
   }
-  RT_CUDA(cudaDeviceSynchronize());
+  RT_CUDA_OR(cudaDeviceSynchronize(), { rt_estimator_destroy(s); });
   *out = s;
   return RT_OK;
 }
 
 int rt_estimator_destroy(rt_estimator* s) {
   if (!s) return RT_OK;
+  RtDeviceGuard on_device(s->device);
   void* ptrs[] = {s->value, s->key, s->next, s->head, s->klen, s->used, s->maxmin};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -657,6 +674,7 @@ int rt_estimator_destroy(rt_estimator* s) {
 
 int rt_estimator_reset(rt_estimator* s, void* stream) {  // estimator.py:25-29
   if (!s) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(s->device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t nk = (size_t)s->n * s->n_keys;
   RT_CUDA(cudaMemsetAsync(s->head, 0, nk * 4, st));
@@ -669,6 +687,7 @@ int rt_estimator_reset(rt_estimator* s, void* stream) {  // estimator.py:25-29
 int rt_estimator_update(rt_estimator* s, const int32_t* key_dev, const double* value_dev, double* est_dev,
                         int32_t* err_dev, void* stream) {
   if (!s || !key_dev || !value_dev) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(s->device);
   k_est_update<<<(unsigned)((s->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*s, key_dev, value_dev,
                                                                               est_dev, err_dev);
   RT_CUDA_LAUNCH_CHECK();
@@ -678,6 +697,7 @@ int rt_estimator_update(rt_estimator* s, const int32_t* key_dev, const double* v
 int rt_estimator_estimate(rt_estimator* s, const int32_t* key_dev, double* est_dev, int32_t* err_dev,
                           void* stream) {
   if (!s || !key_dev || !est_dev) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(s->device);
   k_est_estimate<<<(unsigned)((s->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*s, key_dev, est_dev,
                                                                                 err_dev);
   RT_CUDA_LAUNCH_CHECK();
@@ -687,6 +707,7 @@ int rt_estimator_estimate(rt_estimator* s, const int32_t* key_dev, double* est_d
 int rt_estimator_buffer(rt_estimator* s, const int32_t* key_dev, double* out_dev, int32_t* n_out_dev,
                         int32_t max_out, int32_t* err_dev, void* stream) {
   if (!s || !key_dev || !out_dev || !n_out_dev || max_out < 1) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(s->device);
   k_est_buffer<<<(unsigned)((s->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*s, key_dev, out_dev,
                                                                               n_out_dev, max_out, err_dev);
   RT_CUDA_LAUNCH_CHECK();
@@ -695,6 +716,7 @@ int rt_estimator_buffer(rt_estimator* s, const int32_t* key_dev, double* out_dev
 
 int rt_estimator_maxmin(rt_estimator* s, void** maxmin_dev) {
   if (!s || !maxmin_dev) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(s->device);
   *maxmin_dev = s->maxmin;
   return RT_OK;
 }

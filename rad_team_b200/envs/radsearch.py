@@ -167,7 +167,7 @@ class BatchedRadSearchEnv:
         dt, shp = _BUF_SPEC[name]
         shape = shp(self.E, self.A, self.G * self.G, self.cfg.max_steps * self.A)
         n = int(np.prod(shape))
-        assert n * _ITEMSIZE[dt] == nbytes.value, (name, shape, nbytes.value)
+        _lib.require(n * _ITEMSIZE[dt] == nbytes.value, f"{name}: shape {shape} does not match {nbytes.value} bytes")
 
         class _Arr:  # __cuda_array_interface__ carrier
             pass
@@ -223,8 +223,9 @@ class BatchedRadSearchEnv:
             _lib.check(self._L.rt_env_set_rollout(self._h, None))
             return
         t = self._torch
-        assert readings.is_cuda and readings.dtype == t.float32 and readings.is_contiguous()
-        assert tuple(readings.shape) == (self.cfg.max_steps, self.E, self.A)
+        _lib.require(readings.is_cuda and readings.dtype == t.float32 and readings.is_contiguous()
+                     and tuple(readings.shape) == (self.cfg.max_steps, self.E, self.A),
+                     "rollout readings must be a contiguous float32 CUDA tensor [max_steps, E, A]")
         self._rollout = readings
         _lib.check(self._L.rt_env_set_rollout(self._h, readings.data_ptr()))
 
@@ -250,8 +251,9 @@ class BatchedRadSearchEnv:
         m = self.obs_maps if out_maps is None else out_maps
         if m is None:
             return None, None
-        assert m.is_cuda and m.dtype == self._torch.float32 and m.is_contiguous()
-        assert m.numel() == self.E * 3 * self.G * self.G
+        _lib.require(m.is_cuda and m.dtype == self._torch.float32 and m.is_contiguous()
+                     and m.numel() == self.E * 3 * self.G * self.G and m.device == self.device,
+                     "obs maps must be a contiguous float32 tensor [E, 3, G, G] on the env's device")
         return m, m.data_ptr()
 
     def _info(self, xy, maps) -> Dict[str, Any]:
@@ -299,12 +301,16 @@ class BatchedRadSearchEnv:
         maps, mptr = self._maps_ptr(out_maps) if rasterize else (None, None)
         with self._on_device():
             if isinstance(actions, torch.Tensor) and actions.is_cuda:
-                assert actions.dtype == torch.int32 and actions.is_contiguous() and actions.numel() == self.E * self.A
+                _lib.require(actions.dtype == torch.int32 and actions.is_contiguous()
+                             and actions.numel() == self.E * self.A and actions.device == self.device,
+                             "actions must be a contiguous int32 tensor [E, A] on the env's device")
                 xy = self.obs_xy if out_xy is None else out_xy
                 rw = self.reward if out_reward is None else out_reward
                 dn = self.done if out_done is None else out_done
                 for t_, dt_, n_ in ((xy, torch.int32, 2), (rw, torch.int32, 1), (dn, torch.uint8, 1)):
-                    assert t_.is_cuda and t_.dtype == dt_ and t_.is_contiguous() and t_.numel() == self.E * self.A * n_
+                    _lib.require(t_.is_cuda and t_.dtype == dt_ and t_.is_contiguous()
+                                 and t_.numel() == self.E * self.A * n_ and t_.device == self.device,
+                                 "step outputs must be contiguous CUDA tensors of the documented dtype and size")
                 _lib.check(self._L.rt_env_step(self._h, actions.data_ptr(), xy.data_ptr(), mptr, rw.data_ptr(),
                                                dn.data_ptr(), self._stream()), "rt_env_step")
                 info = self._info(self.obs_xy, maps)
@@ -313,12 +319,14 @@ class BatchedRadSearchEnv:
                 return xy, rw, dn, False, info
             # host path
             if isinstance(actions, torch.Tensor):
-                assert actions.dtype == torch.int32 and actions.is_contiguous()
+                _lib.require(actions.dtype == torch.int32 and actions.is_contiguous(),
+                             "host actions must be a contiguous int32 tensor")
                 aptr, keep = actions.data_ptr(), actions
             else:
                 keep = np.ascontiguousarray(actions, dtype=np.int32)
                 aptr = keep.ctypes.data
-            assert (keep.numel() if hasattr(keep, "numel") else keep.size) == self.E * self.A
+            _lib.require((keep.numel() if hasattr(keep, "numel") else keep.size) == self.E * self.A,
+                         "actions must hold E * A entries")
             hxy, hrw, hdn = self._host_bufs()
             rc = self._L.rt_env_step_host(self._h, aptr, hxy.data_ptr(), hrw.data_ptr(), hdn.data_ptr(), mptr,
                                           self._stream())

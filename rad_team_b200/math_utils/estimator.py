@@ -44,7 +44,7 @@ class BatchedEstimator:
     def _keys(self, key):
         t = self._torch
         k = t.as_tensor(key, dtype=t.int32, device=self.device).contiguous()
-        assert k.numel() == self.n
+        _lib.require(k.numel() == self.n, "one key per estimator expected")
         return k
 
     def reset(self) -> None:

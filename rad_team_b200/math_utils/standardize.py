@@ -40,7 +40,7 @@ class BatchedWelford:
     def _as_f64(self, x):
         t = self._torch
         x = t.as_tensor(x, dtype=t.float64, device=self.device).contiguous()
-        assert x.numel() == self.n
+        _lib.require(x.numel() == self.n, "one reading per stream expected")
         return x
 
     def reset(self) -> None:
@@ -147,13 +147,17 @@ class RunningMoments:
 
     def update(self, x) -> None:
         t = self._torch
-        assert x.is_cuda and x.dtype == t.float32 and x.is_contiguous()
+        _lib.require(x.is_cuda and x.dtype == t.float32 and x.is_contiguous(),
+                     "readings must be a contiguous float32 CUDA tensor")
         _lib.check(self._L.rt_moments_update(self._h, x.data_ptr(), x.numel(), self._stream()), "rt_moments_update")
 
     def standardize(self, x, out=None):
         t = self._torch
-        assert x.is_cuda and x.dtype == t.float32 and x.is_contiguous()
+        _lib.require(x.is_cuda and x.dtype == t.float32 and x.is_contiguous(),
+                     "readings must be a contiguous float32 CUDA tensor")
         out = t.empty_like(x) if out is None else out
+        _lib.require(out.is_cuda and out.dtype == t.float32 and out.is_contiguous() and out.numel() == x.numel(),
+                     "out must be a contiguous float32 CUDA tensor of the input's size")
         _lib.check(self._L.rt_moments_standardize(self._h, x.data_ptr(), out.data_ptr(), x.numel(), self._stream()))
         return out
 
@@ -161,7 +165,8 @@ class RunningMoments:
         """state <- Chan merge, in rank order, of gathered float64 [n_ranks, >=3] (device): row r starts
         with rank r's (count, mean, M2)."""
         t = self._torch
-        assert gathered.is_cuda and gathered.dtype == t.float64 and gathered.is_contiguous() and gathered.dim() == 2
+        _lib.require(gathered.is_cuda and gathered.dtype == t.float64 and gathered.is_contiguous()
+                     and gathered.dim() == 2, "gathered must be a contiguous float64 CUDA tensor [n_ranks, >=3]")
         _lib.check(self._L.rt_moments_merge(self._h, gathered.data_ptr(), gathered.shape[0], gathered.shape[1],
                                             self._stream()))
 

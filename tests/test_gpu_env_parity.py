@@ -15,13 +15,13 @@ STATE = ["AGENT_XY", "PREV_DIST", "START_XY", "SRC_XY", "SRC_INT", "BKG", "N_POL
 RTOL = 1e-5  # the stated tolerance; exact equality is asserted first
 
 
-def make_pair(**cfg):
+def make_pair(device=None, **cfg):
     from oracle import oracle as O
     from rad_team_b200.envs import BatchedRadSearchEnv
 
     full = dict(O.DEFAULTS)
     full.update(cfg)
-    return BatchedRadSearchEnv(**full), O.OracleEnv(**full)
+    return BatchedRadSearchEnv(device=device, **full), O.OracleEnv(**full)
 
 
 def assert_state_equal(g, o, names=STATE, where=""):
@@ -435,3 +435,16 @@ def test_incremental_observation_update_matches_full_rasterisation():
     assert full.errors() == inc.errors()
     for k in ("VISIT", "INTENSITY", "VREC"):
         assert torch.equal(full.buffer(k), inc.buffer(k)), k
+
+
+def test_handle_runs_on_its_creation_device():
+    """include/rt_b200.h conventions: entry points run on the handle's device, not the caller's current one."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    g, o = make_pair(device=1, n_envs=64, n_agents=2, grid=16, max_steps=12, seed=5)
+    torch.cuda.set_device(0)
+    run_episode(g, o, 8, np.random.default_rng(0))
+    assert torch.cuda.current_device() == 0
+    g.close()
