@@ -22,7 +22,7 @@ import torch.nn.functional as F
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from rad_team_b200.distributed import merge_rollout_stats  # noqa: E402
-from rad_team_b200.envs import BatchedRadSearchEnv  # noqa: E402
+from rad_team_b200.envs import BatchedRadSearchEnv, obs_tensor  # noqa: E402
 from rad_team_b200.math_utils import RunningMoments  # noqa: E402
 
 
@@ -73,7 +73,7 @@ def main():
     opt = torch.optim.Adam(model.parameters(), lr=3e-4)
     amp = torch.bfloat16 if args.dtype == "bf16" else torch.float32
 
-    obs = torch.empty((T + 1, E, 3, G, G), dtype=torch.float32, device=dev)   # rollout slots = env outputs
+    obs = obs_tensor((T + 1, E, 3, G, G), device=dev, zero=False)   # rollout slots = env outputs, compressible HBM
     xy = torch.empty((T + 1, E, A, 2), dtype=torch.int32, device=dev)
     rd = torch.zeros((T + 1, E, A), dtype=torch.float32, device=dev)
     act = torch.empty((T, E, A), dtype=torch.int64, device=dev)

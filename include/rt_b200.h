@@ -233,6 +233,21 @@ int rt_env_errors(rt_env* env, int32_t* flags_host, void* stream);
 /* Number of kernels this handle has launched so far (bench bookkeeping). */
 int64_t rt_env_launch_count(const rt_env* env);
 
+/* ---- observation-tensor memory ---------------------------------------------
+ * north_star: "writes directly into the CNN input tensor" — the tensor is the
+ * caller's.  These two calls let the caller place it in COMPRESSIBLE device
+ * memory (driver virtual-memory API, CU_MEM_ALLOCATION_COMP_GENERIC): the maps
+ * are mostly zeros, and Blackwell's L2 compresses such lines on their way to
+ * HBM, which shortens both the rasteriser's store stream and the consumer's
+ * read pass.  Any device memory works with rt_env_step; this is an option, not
+ * a requirement.  The block lives on the current device; contents are
+ * uninitialised.  *compressible_out (may be NULL) = 1 when compressible backing
+ * was granted, 0 when the device (or RT_B200_OBS_COMPRESS=0) gave plain memory.
+ * rt_obs_free synchronises that device, then unmaps and releases the block;
+ * a pointer that did not come from rt_obs_alloc is RT_ERR_BAD_ARG. */
+int rt_obs_alloc(size_t bytes, void** dev_ptr, int32_t* compressible_out);
+int rt_obs_free(void* dev_ptr);
+
 /* ---- WelfordsOnlineStandardization: src/math_utils/standardize.py:7-107 --- */
 
 /* n independent streams, each with the reference's exact sequential state. */

@@ -57,6 +57,8 @@ SYMBOLS = {
     "rt_env_buffer": (C.c_int, [_vp, C.c_int, _pp, C.POINTER(C.c_size_t)]),
     "rt_env_errors": (C.c_int, [_vp, C.POINTER(_i32), _vp]),
     "rt_env_launch_count": (_i64, [_vp]),
+    "rt_obs_alloc": (C.c_int, [C.c_size_t, _pp, C.POINTER(_i32)]),
+    "rt_obs_free": (C.c_int, [_vp]),
     "rt_welford_create": (C.c_int, [_i64, _pp]),
     "rt_welford_destroy": (C.c_int, [_vp]),
     "rt_welford_reset": (C.c_int, [_vp, _vp]),

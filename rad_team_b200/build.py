@@ -17,7 +17,7 @@ CSRC = PKG / "csrc"
 INCLUDE = PKG.parent / "include"
 LIB = PKG / "librt_b200.so"
 
-SOURCES = ["rt_host.cu", "rt_env.cu", "rt_stats.cu"]
+SOURCES = ["rt_host.cu", "rt_alloc.cu", "rt_env.cu", "rt_stats.cu"]
 HEADERS = ["rt_host.h", "rt_device.cuh", "rt_env_kernels.cuh"]
 
 NVCC_FLAGS = [

@@ -19,6 +19,7 @@ struct rt_env {
   int device = 0;
   int n_sm = 148;
   void* slab = nullptr;  // one allocation, carved at 256 B granularity
+  bool slab_vmm = false; // RT_B200_SLAB_COMPRESS=1: the slab came from rt_obs_alloc (compressible memory)
   size_t slab_bytes = 0;
   void* buf_ptr[RT_BUF__COUNT] = {};
   size_t buf_bytes[RT_BUF__COUNT] = {};
@@ -43,6 +44,7 @@ struct rt_env {
   bool sparse = true;                       // RT_B200_RASTER=dense selects the dense (LSU) rasteriser
   int sparse_ctas = 24;                     // k_raster_sparse_lsu: CTAs (8 warp pipelines each) per SM in the grid (2 resident)
   bool sparse_lsu = true;                   // RT_B200_RASTER=sparse_tma selects the bulk-store variant
+  bool pdl = true;                          // RT_B200_PDL=0: plain stream-ordered launches of k_step / the rasteriser
   int sparse_hints = 19;                    // bit 0/1: TMA variant L2 hints; bit 4: plain st.global (else .cs) in the LSU variant
 };
 
@@ -56,6 +58,24 @@ struct Carver {
     return at;
   }
 };
+
+// Launch with (optionally) the programmatic-stream-serialisation attribute: the kernel's CTAs may be scheduled
+// while the previous kernel of the stream drains; the kernel itself calls pdl_wait() before touching its inputs.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, bool pdl,
+                       Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 bool is_pinned_or_device(const void* p) {
   cudaPointerAttributes at;
@@ -158,7 +178,8 @@ int launch_raster(rt_env* h, float* obs_maps, cudaStream_t st) {
     const size_t smb = raster_sl_smem_bytes(d.cells, 0);
     long long nb = (long long)h->n_sm * h->sparse_ctas;
     if (nb * kSlWarps > d.E) nb = (d.E + kSlWarps - 1) / kSlWarps;
-    k_raster_sparse_lsu<false><<<(unsigned)nb, kSlThreads, smb, st>>>(d, obs_maps, h->sparse_hints & 16);
+    RT_CUDA(launch_pdl(k_raster_sparse_lsu<false>, (unsigned)nb, kSlThreads, smb, st, h->pdl, d, obs_maps,
+                       h->sparse_hints & 16));
   } else if (h->sparse) {
     const size_t smb = raster_sparse_smem_bytes(d.cells, d.rec_prefix, h->lut_in_smem ? d.cap + 1 : 0);
     long long nb = (long long)h->n_sm;  // 16 tiles fill an SM's shared memory: one persistent CTA each
@@ -198,7 +219,8 @@ int launch_step(rt_env* h, const int32_t* actions, int32_t* obs_xy, float* obs_m
   const EnvDev& d = h->dev;
   const int epb = h->epb;
   const unsigned blocks = (unsigned)((d.E + epb - 1) / epb);
-  k_step<<<blocks, epb * d.A, step_smem_bytes(epb, d.A), st>>>(d, actions, obs_xy, reward, done);
+  RT_CUDA(launch_pdl(k_step, blocks, (unsigned)(epb * d.A), step_smem_bytes(epb, d.A), st, h->pdl, d, actions, obs_xy,
+                     reward, done));
   h->launches += 1;
   RT_CUDA_LAUNCH_CHECK();
   if (obs_maps) return raster_or_patch(h, obs_maps, st);
@@ -281,12 +303,19 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
   const size_t o_act = cv.take(E * A * 4), o_xy = cv.take(E * A * 8), o_rw = cv.take(E * A * 4),
                o_dn = cv.take(E * A), o_mask = cv.take(E), o_for = cv.take(16), o_prev = cv.take(E * 16);
   h->slab_bytes = cv.off;
-  if (cudaMalloc(&h->slab, h->slab_bytes) != cudaSuccess) {
+  if (const char* ev = std::getenv("RT_B200_SLAB_COMPRESS")) h->slab_vmm = std::atoi(ev) != 0;
+  if (h->slab_vmm) {
+    const int rc = rt_obs_alloc(h->slab_bytes, &h->slab, nullptr);
+    if (rc != RT_OK) {
+      delete h;
+      return rc;
+    }
+  } else if (cudaMalloc(&h->slab, h->slab_bytes) != cudaSuccess) {
     rt_note_cuda_error(cudaGetLastError(), "cudaMalloc(slab)");
     delete h;
     return RT_ERR_NOMEM;
   }
-  RT_CUDA_OR(cudaMemset(h->slab, 0, h->slab_bytes), { cudaFree(h->slab); delete h; });
+  RT_CUDA_OR(cudaMemset(h->slab, 0, h->slab_bytes), { rt_env_destroy(h); });
   unsigned char* base = (unsigned char*)h->slab;
   for (int i = 0; i < RT_BUF__COUNT; ++i) {
     h->buf_ptr[i] = sz[i] ? base + off[i] : nullptr;
@@ -301,8 +330,7 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
 
   // pinned staging: actions | obs_xy | reward | done | mask
   h->pinned_bytes = E * A * 4 + E * A * 8 + E * A * 4 + E * A + E + 64;
-  RT_CUDA_OR(cudaHostAlloc((void**)&h->pinned, h->pinned_bytes, cudaHostAllocDefault),
-             { cudaFree(h->slab); delete h; });
+  RT_CUDA_OR(cudaHostAlloc((void**)&h->pinned, h->pinned_bytes, cudaHostAllocDefault), { rt_env_destroy(h); });
 
   EnvDev& d = h->dev;
   d.E = cfg->n_envs; d.A = cfg->n_agents; d.G = cfg->grid; d.cells = (int)cells;
@@ -394,6 +422,7 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
   if (const char* ev = std::getenv("RT_B200_RASTER_UNROLL")) h->raster_unroll = std::max(1, std::atoi(ev));
   if (const char* ev = std::getenv("RT_B200_SPARSE_CTAS")) h->sparse_ctas = std::max(1, std::atoi(ev));
   if (const char* ev = std::getenv("RT_B200_SPARSE_HINTS")) h->sparse_hints = std::atoi(ev);
+  if (const char* ev = std::getenv("RT_B200_PDL")) h->pdl = std::atoi(ev) != 0;
   if (const char* ev = std::getenv("RT_B200_RASTER")) {
     h->sparse = std::strcmp(ev, "dense") != 0;
     h->sparse_lsu = std::strcmp(ev, "sparse_tma") != 0;
@@ -431,7 +460,8 @@ int rt_env_destroy(rt_env* h) {
     cudaStreamDestroy(h->aux);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  if (h->slab) cudaFree(h->slab);
+  if (h->slab && h->slab_vmm) rt_obs_free(h->slab);
+  else if (h->slab) cudaFree(h->slab);
   if (h->pinned) cudaFreeHost(h->pinned);
   delete h;
   return RT_OK;

@@ -73,6 +73,12 @@ struct EnvDev {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialisation attribute may have
+// its CTAs scheduled while the previous kernel in the stream drains; pdl_wait() blocks until that kernel has
+// completed and its writes are visible, pdl_launch_dependents() lets the NEXT kernel's CTAs start early in turn.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -452,6 +458,8 @@ __global__ void __launch_bounds__(192, RT_STEP_MIN_CTAS)
 k_step(const EnvDev d, const int32_t* __restrict__ actions, int32_t* __restrict__ obs_xy,
        int32_t* __restrict__ reward, uint8_t* __restrict__ done) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_launch_dependents();
+  pdl_wait();  // the rasteriser of the previous step still reads the records this kernel updates
   step_tile(d, actions, obs_xy, reward, done, smem_raw);
 }
 
@@ -845,7 +853,7 @@ __host__ __device__ inline size_t raster_sl_smem_bytes(int cells, int lut_entrie
 template <bool kLutInSmem>
 __global__ void __launch_bounds__(kSlThreads)
 k_raster_sparse_lsu(const EnvDev d, float* __restrict__ out, int plain_stores) {
-  extern __shared__ __align__(16) unsigned char sm[];
+  extern __shared__ __align__(128) unsigned char sm[];
   const int cells = d.cells, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   float* tile = reinterpret_cast<float*>(sm + (size_t)w * cells * 12);
   float* s_lut = reinterpret_cast<float*>(sm + (size_t)kSlWarps * cells * 12);
@@ -853,9 +861,11 @@ k_raster_sparse_lsu(const EnvDev d, float* __restrict__ out, int plain_stores) {
     for (int i = tid; i <= d.cap; i += kSlThreads) s_lut[i] = d.lut[i];
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const int n4 = (cells * 3) >> 2;  // float4 per tile
+  pdl_launch_dependents();
   for (int i = lane; i < n4; i += 32) reinterpret_cast<float4*>(tile)[i] = z4;
   __syncthreads();  // table staged (the only CTA-wide barrier)
   const float* lut = kLutInSmem ? s_lut : d.lut;
+  pdl_wait();  // tiles are zeroed while the step kernel drains; its records are read from here on
 
   // Static strided assignment: warp gw takes envs gw, gw + n_warps, ...  The grid is deliberately MANY
   // short-lived CTAs (24 per SM, 2 resident): measured best — persistent CTAs leave a tail of stragglers,

@@ -7,6 +7,7 @@
 // Last CUDA failure seen by this library (for rt_status_string(RT_ERR_CUDA)).
 const char* rt_last_cuda_error();
 void rt_note_cuda_error(cudaError_t err, const char* what);
+void rt_note_error_text(const char* text);
 
 // A handle belongs to the device that was current when it was created; its entry points run there
 // whatever device the calling thread has selected since, and restore the caller's choice on return.

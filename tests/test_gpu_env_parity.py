@@ -448,3 +448,46 @@ def test_handle_runs_on_its_creation_device():
     run_episode(g, o, 8, np.random.default_rng(0))
     assert torch.cuda.current_device() == 0
     g.close()
+
+
+def test_observation_memory_allocator():
+    """rt_obs_alloc / rt_obs_free (include/rt_b200.h): compressible observation memory behaves like any
+    device memory — the rasteriser writes the same bytes into it, torch reads it, and it outlives the
+    Python handle that created it for as long as a tensor uses it."""
+    import ctypes as C
+    import gc
+
+    import torch
+
+    from rad_team_b200 import _lib
+    from rad_team_b200.envs import obs_tensor
+
+    g, o = make_pair(n_envs=96, n_agents=3, grid=32, max_steps=40, seed=11)
+    assert g.obs_maps.is_cuda and hasattr(g.obs_maps, "rt_compressible")
+    plain = torch.empty_like(g.obs_maps)          # ordinary caching-allocator memory
+    mine = obs_tensor(g.obs_maps.shape, zero=False)
+    g.reset(out_maps=mine)
+    o.reset()
+    rng = np.random.default_rng(3)
+    for t in range(12):
+        act = rng.integers(1, 5, size=(96, 3)).astype(np.int32)
+        g.step(torch.as_tensor(act, device=g.device), out_maps=mine)
+        g.rasterize(plain)
+        _, m_o, _, _ = o.step(act, maps=True)
+        assert torch.equal(mine, plain)
+        assert np.array_equal(mine.cpu().numpy(), m_o)
+    view = mine[5:7]
+    del mine
+    gc.collect()
+    assert float(view.sum()) == float(plain[5:7].sum())   # the block is still mapped under the view
+    del view
+    gc.collect()
+    # C ABI contract: foreign pointers are refused, NULL is a no-op, zero bytes is a bad argument
+    L = _lib.lib()
+    assert L.rt_obs_free(C.c_void_p(plain.data_ptr())) == _lib.RT_ERR_BAD_ARG
+    assert L.rt_obs_free(None) == _lib.RT_OK
+    p = C.c_void_p()
+    assert L.rt_obs_alloc(0, C.byref(p), None) == _lib.RT_ERR_BAD_ARG
+    assert L.rt_obs_alloc(1 << 20, C.byref(p), None) == _lib.RT_OK and p.value
+    assert L.rt_obs_free(p) == _lib.RT_OK
+    assert L.rt_obs_free(p) == _lib.RT_ERR_BAD_ARG   # double free is caught, not executed
