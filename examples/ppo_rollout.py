@@ -22,7 +22,8 @@ import torch.nn.functional as F
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from rad_team_b200.distributed import merge_rollout_stats  # noqa: E402
-from rad_team_b200.envs import BatchedRadSearchEnv, obs_tensor  # noqa: E402
+from rad_team_b200.envs import BatchedRadSearchEnv  # noqa: E402
+from rad_team_b200.memory import obs_tensor, readings_tensor  # noqa: E402
 from rad_team_b200.math_utils import RunningMoments  # noqa: E402
 
 
@@ -81,7 +82,7 @@ def main():
     val = torch.empty((T + 1, E, A), dtype=torch.float32, device=dev)
     rew = torch.empty((T, E, A), dtype=torch.int32, device=dev)    # written by the env, slot by slot
     dn = torch.empty((T, E, A), dtype=torch.uint8, device=dev)
-    readings = torch.zeros((120, E, A), dtype=torch.float32, device=dev)
+    readings = readings_tensor((120, E, A), device=dev)
     env.set_rollout(readings)
     moments = RunningMoments()
 

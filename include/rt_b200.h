@@ -239,7 +239,8 @@ int64_t rt_env_launch_count(const rt_env* env);
  * memory (driver virtual-memory API, CU_MEM_ALLOCATION_COMP_GENERIC): the maps
  * are mostly zeros, and Blackwell's L2 compresses such lines on their way to
  * HBM, which shortens both the rasteriser's store stream and the consumer's
- * read pass.  Any device memory works with rt_env_step; this is an option, not
+ * read pass.  The same holds for rollout buffers of Poisson readings (small
+ * integers stored as float32, rt_env_set_rollout / rt_moments_update).  Any device memory works with rt_env_step; this is an option, not
  * a requirement.  The block lives on the current device; contents are
  * uninitialised.  *compressible_out (may be NULL) = 1 when compressible backing
  * was granted, 0 when the device (or RT_B200_OBS_COMPRESS=0) gave plain memory.

@@ -20,6 +20,7 @@ from typing import Any, Dict, Optional, Tuple
 import numpy as np
 
 from .. import _lib
+from ..memory import obs_tensor
 
 
 @dataclass
@@ -92,48 +93,6 @@ class _NullCtx:
 
 
 _NULL_CTX = _NullCtx()
-
-
-class _ObsBlock:
-    """Owner of one rt_obs_alloc block; tensors built on it keep it alive (``__cuda_array_interface__``)."""
-
-    def __init__(self, nbytes: int, shape, typestr: str) -> None:
-        self._L = _lib.lib()
-        ptr, comp = C.c_void_p(), C.c_int32(0)
-        _lib.check(self._L.rt_obs_alloc(nbytes, C.byref(ptr), C.byref(comp)), "rt_obs_alloc")
-        self._ptr = ptr
-        self.compressible = bool(comp.value)
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr.value, False),
-                                          "version": 2, "strides": None}
-
-    def __del__(self) -> None:  # pragma: no cover - runs when the last tensor on the block dies
-        try:
-            if self._ptr.value:
-                self._L.rt_obs_free(self._ptr)
-                self._ptr = C.c_void_p()
-        except Exception:
-            pass
-
-
-def obs_tensor(shape, device=None, zero: bool = True):
-    """float32 CUDA tensor for observation maps in compressible device memory (rt_obs_alloc): the maps are
-    mostly zeros, which the B200's L2 compresses on the way to HBM — the rasteriser writes it, and a network
-    reads it, faster than a ``torch.empty`` tensor.  Use it for ``out_maps`` targets and rollout observation
-    buffers; ``tensor.rt_compressible`` says whether the device granted compressible backing."""
-    torch = _lib.require_cuda()
-    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    if dev.index is None:
-        dev = torch.device("cuda", torch.cuda.current_device())
-    shape = tuple(int(x) for x in shape)
-    n = int(np.prod(shape))
-    _lib.require(n > 0, "obs_tensor needs a non-empty shape")
-    with torch.cuda.device(dev):
-        block = _ObsBlock(n * 4, shape, "<f4")
-        t = torch.as_tensor(block, device=dev)
-        if zero:
-            t.zero_()
-    t.rt_compressible = block.compressible
-    return t
 
 
 class BatchedRadSearchEnv:

@@ -460,7 +460,7 @@ def test_observation_memory_allocator():
     import torch
 
     from rad_team_b200 import _lib
-    from rad_team_b200.envs import obs_tensor
+    from rad_team_b200.memory import compressible_tensor, obs_tensor
 
     g, o = make_pair(n_envs=96, n_agents=3, grid=32, max_steps=40, seed=11)
     assert g.obs_maps.is_cuda and hasattr(g.obs_maps, "rt_compressible")
@@ -482,6 +482,8 @@ def test_observation_memory_allocator():
     assert float(view.sum()) == float(plain[5:7].sum())   # the block is still mapped under the view
     del view
     gc.collect()
+    ints = compressible_tensor((1000, 3), dtype=torch.int32)
+    assert ints.dtype == torch.int32 and int(ints.sum()) == 0 and tuple(ints.shape) == (1000, 3)
     # C ABI contract: foreign pointers are refused, NULL is a no-op, zero bytes is a bad argument
     L = _lib.lib()
     assert L.rt_obs_free(C.c_void_p(plain.data_ptr())) == _lib.RT_ERR_BAD_ARG
