@@ -201,7 +201,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": rate, "unit": "agent-env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -451,12 +451,33 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "error_flags": flags,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries also write there (NCCL prints its version banner
+    on first use when NCCL_DEBUG is set), so file descriptor 1 is pointed at stderr for the whole run and the
+    JSON line alone goes to the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1200)
