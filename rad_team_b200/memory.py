@@ -9,6 +9,7 @@ GiB.  The tensors behave like any CUDA tensor; the block is unmapped when the la
 from __future__ import annotations
 
 import ctypes as C
+import warnings
 
 import numpy as np
 
@@ -52,7 +53,13 @@ def compressible_tensor(shape, dtype=None, device=None, zero: bool = True):
     n = int(np.prod(shape))
     _lib.require(n > 0, "compressible_tensor needs a non-empty shape")
     with torch.cuda.device(dev):
-        block = _Block(n * np.dtype(_TYPESTR[name]).itemsize, shape, _TYPESTR[name])
+        try:
+            block = _Block(n * np.dtype(_TYPESTR[name]).itemsize, shape, _TYPESTR[name])
+        except _lib.RtError as exc:  # no virtual-memory API on this driver: ordinary device memory serves as well
+            warnings.warn(f"rt_obs_alloc unavailable ({exc}); using the torch allocator", RuntimeWarning, stacklevel=2)
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=dev)
+            t.rt_compressible = False
+            return t
         t = torch.as_tensor(block, device=dev)
         if zero:
             t.zero_()
