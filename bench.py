@@ -446,7 +446,9 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_bytes_per_step": E * A * 13, "steps": K2,
                     "note": "rt_env_step_host per step: pinned int32 actions cross PCIe every step (k_step reads the mapped "
                             "buffer in place, no staging copy); obs_xy, reward, done are copied down on an auxiliary "
-                            "stream under the rasteriser; maps are rasterised into the device-resident CNN input tensor"},
+                            "stream under the rasteriser and the call returns when they have landed; maps are rasterised into the "
+                            "device-resident CNN input tensor in stream order (the timed region ends with a device synchronise, "
+                            "so every rasterisation is inside it)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "error_flags": flags,

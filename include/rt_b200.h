@@ -187,8 +187,11 @@ int rt_env_step(rt_env* env, const int32_t* actions_dev, int32_t* obs_xy_dev, fl
  * CNN's input tensor).  Pinned caller buffers are used directly (the step
  * kernel reads pinned actions in place over PCIe), pageable ones go through
  * pinned staging owned by the handle; the results travel back on an internal
- * stream while the rasteriser runs, and the call returns after they have
- * landed.  rt_env_step_host returns RT_ERR_BAD_ACTION when an action was
+ * stream while the rasteriser runs, and the call returns as soon as they have
+ * landed: the rasterisation of obs_maps_dev may still be in flight on `stream`
+ * (it is ordered before anything enqueued there later — the consumer network,
+ * the next step — so the host's work between two steps hides under it).
+ * rt_env_step_host returns RT_ERR_BAD_ACTION when an action was
  * outside 1..4: the steps of exactly those envs were voided (no state change,
  * as in the reference, which raises before touching state); every other env
  * advanced and all outputs are valid. */

@@ -579,8 +579,10 @@ int rt_env_step_host(rt_env* h, const int32_t* actions_host, int32_t* obs_xy_hos
     rc = raster_or_patch(h, obs_maps_dev, st);
     if (rc != RT_OK) return rc;
   }
+  // Return when the step's results are in host memory.  The rasteriser keeps streaming on `st`: whatever
+  // the host does before its next call (the policy's bookkeeping, the next call's own launch latency) hides
+  // under it, and everything enqueued on `st` later is ordered behind it.
   RT_CUDA(cudaStreamSynchronize(h->aux));
-  RT_CUDA(cudaStreamSynchronize(st));
   if (!dx) std::memcpy(obs_xy_host, p_xy, n * 8);
   if (!dr) std::memcpy(reward_host, p_rw, n * 4);
   if (!dd) std::memcpy(done_host, p_dn, n);
