@@ -7,6 +7,7 @@ There is deliberately no CPU fallback.  If the shared library is missing it is r
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 from . import build as _build
@@ -95,7 +96,10 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is None:
         path = _build.LIB
-        if not path.exists():
+        alt = os.environ.get("RT_B200_LIB")  # A/B builds of the SAME library (tools/, profiles/ sweeps), never a fallback
+        if alt:
+            path = Path(alt)
+        elif not path.exists():
             _build.build()  # raises RuntimeError without nvcc: no silent fallback
         try:
             L = C.CDLL(str(path))

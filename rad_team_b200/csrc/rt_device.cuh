@@ -185,6 +185,77 @@ __device__ __forceinline__ double dloggam(double x) {
 }
 
 // ---------------------------------------------------------------------------
+// Squeeze for the PTRS acceptance test  log V + log(1/alpha) - log(a/us^2 + b) <= -lam + k log lam - lgamma(k+1).
+// The exact test (four dlog, the log-gamma series, three divisions: a ~450-instruction dependent fp64 chain run
+// by a handful of lanes while the rest of the warp waits) was a quarter of k_step's time.  Here both sides are
+// evaluated APPROXIMATELY — single-precision lg2.approx for the logarithms, three Stirling terms for lgamma —
+// together with a rigorous bound `margin` on |approximate difference - the difference the exact code computes|.
+// Only when the approximate difference clears the margin is the decision taken from it (it is then the same
+// decision, on any hardware); otherwise the caller evaluates the exact test.  Returns +1 accept, -1 reject,
+// 0 undecided.
+//
+// Error budget (natural-log units).  flog(x) = ln2 * lg2.approx((float)x): rounding x to float moves ln x by
+// <= 2^-24; lg2.approx.f32 is within 2^-22 absolute on [0.5, 2] and 2 ulp (<= 2^-22 |result|) elsewhere, so
+// |flog(x) - ln x| <= 2^-21 (1 + |ln x|).  The code charges c = 2^-20 per unit and then multiplies the whole
+// budget by 4.  The float argument a/us^2 + b carries seven roundings (<= 7 * 2^-24 in its logarithm, which is
+// >= 2.2: still inside 2^-21 (1 + |ln|)).  ln(k+1) is taken as loglam (the exact test's own value) + flog((k+1)/lam)
+// with the quotient formed in float (three roundings); it enters lgamma multiplied by (k + 1/2), so its error is
+// charged x-fold.  Stirling's series cut after 1/(360 x^3) is within 1/(1260 x^5) < 2.5e-8 for x >= 8; below
+// that ln k! comes from a table.  The fp64 evaluation error of either side (exact code or this one) is below
+// 2^-45 of the sum of the magnitudes of its terms; 2^-40 is charged.
+// (tests/test_squeeze_margin.py replays this budget on the CPU against an adversarial logarithm.)
+__device__ __forceinline__ float flog2_approx(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ int ptrs_squeeze(double V, double us, double a, double b, double invalpha, double lam,
+                                            double loglam, long long k) {
+  const double ln2 = 6.93147180559945286227e-01, c = 9.5367431640625e-07 /* 2^-20 */;
+  const double x = (double)(k + 1);
+  const float usf = (float)us;
+  const float wf = __fadd_rn(__fdiv_rn((float)a, __fmul_rn(usf, usf)), (float)b);
+  const double Lv = __dmul_rn(ln2, (double)flog2_approx((float)V));
+  const double Li = __dmul_rn(ln2, (double)flog2_approx((float)invalpha));
+  const double Lw = __dmul_rn(ln2, (double)flog2_approx(wf));
+  double G, gerr, gmag;  // lgamma(k + 1), the bound on its error (before the factor 4), its magnitude terms
+  if (k < 7) {
+    // ln k! for k = 0..6, correctly rounded
+    const double lf = k < 2 ? 0.0 : k == 2 ? 6.93147180559945286227e-01 : k == 3 ? 1.79175946922805495731e+00
+                    : k == 4 ? 3.17805383034794575181e+00 : k == 5 ? 4.78749174278204581157e+00
+                             : 6.57925121201010121297e+00;
+    G = lf;
+    gerr = 0.0;
+    gmag = lf;
+  } else {
+    // ln x = ln lam (the exact test's own value) + ln(x / lam), the quotient formed in float
+    const double Lq = __dmul_rn(ln2, (double)flog2_approx(__fdiv_rn((float)x, (float)lam)));
+    const double Lx = __dadd_rn(loglam, Lq);
+    // lgamma(x) ~ (x - 1/2) ln x - x + ln(2 pi)/2 + 1/(12 x) - 1/(360 x^3)
+    const double ix = (double)__frcp_rn((float)x);
+    const double ix3 = __dmul_rn(__dmul_rn(ix, ix), ix);
+    G = __dsub_rn(__dmul_rn(__dsub_rn(x, 0.5), Lx), x);
+    G = __dadd_rn(G, 9.18938533204672669541e-01);
+    G = __dadd_rn(G, __dsub_rn(__dmul_rn(ix, 8.33333333333333287074e-02), __dmul_rn(ix3, 2.77777777777777788381e-03)));
+    gerr = __dmul_rn(__dmul_rn(c, x), __dadd_rn(1.0, fabs(Lq)));
+    gmag = __dadd_rn(__dmul_rn(x, fabs(Lx)), x);
+  }
+  const double kl = __dmul_rn((double)k, loglam);
+  const double lhs = __dsub_rn(__dadd_rn(Lv, Li), Lw);
+  const double rhs = __dsub_rn(__dsub_rn(kl, lam), G);
+  const double diff = __dsub_rn(lhs, rhs);
+  const double logs = __dadd_rn(__dadd_rn(fabs(Lv), fabs(Li)), __dadd_rn(fabs(Lw), 3.0));
+  const double mags = __dadd_rn(__dadd_rn(lam, fabs(kl)), __dadd_rn(gmag, logs));
+  const double margin =
+      __dadd_rn(__dmul_rn(4.0, __dadd_rn(__dadd_rn(__dmul_rn(c, logs), gerr), 1.1920928955078125e-07 /* 2^-23 */)),
+                __dmul_rn(9.094947017729282e-13 /* 2^-40 */, mags));
+  if (!(margin < 1.0)) return 0;  // huge rates, or anything not finite: the exact test decides
+  if (diff < -margin) return 1;
+  if (diff > margin) return -1;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
 // Poisson sampler: Knuth multiplication below 10, Hoermann's PTRS from 10 up —
 // the algorithm numpy.random.Generator.poisson uses, on our uniforms.
 constexpr int kPoissonMaxIters = 1024;
@@ -228,6 +299,13 @@ __device__ __forceinline__ long long poisson_draw(double lam, Draws& d, int& fla
     k = (long long)floor(__dadd_rn(__dadd_rn(__dmul_rn(t, U), lam), 0.43));
     if (us >= 0.07 && V <= vr) return k;
     if (k < 0 || (us < 0.013 && V > us)) continue;
+#ifndef RT_PTRS_NO_SQUEEZE
+    {  // cheap outer test first: decides all but ~1e-4 of the cases that get here, never differently
+      const int sq = ptrs_squeeze(V, us, a, b, invalpha, lam, loglam, k);
+      if (sq > 0) return k;
+      if (sq < 0) continue;
+    }
+#endif
     const double lhs = __dsub_rn(__dadd_rn(dlog(V), dlog(invalpha)),
                                  dlog(__dadd_rn(__ddiv_rn(a, __dmul_rn(us, us)), b)));
     const double rhs = __dsub_rn(__dadd_rn(-lam, __dmul_rn((double)k, loglam)),

@@ -493,3 +493,67 @@ def test_observation_memory_allocator():
     assert L.rt_obs_alloc(1 << 20, C.byref(p), None) == _lib.RT_OK and p.value
     assert L.rt_obs_free(p) == _lib.RT_OK
     assert L.rt_obs_free(p) == _lib.RT_ERR_BAD_ARG   # double free is caught, not executed
+
+
+def test_ptrs_acceptance_threshold_adversarial():
+    """The device sampler decides most PTRS acceptance tests from a cheap approximate evaluation with an error
+    margin (rt_device.cuh: ptrs_squeeze) and only the rest from the exact fdlibm-style test the oracle runs.
+    Injected (U, V) pairs put V at relative distances 1e-15 … 3e-1 on BOTH sides of the acceptance boundary
+    (inside the margin: the exact test must take over; outside: the approximation decides) — every count has
+    to equal the oracle's, and both outcomes have to occur."""
+    import math
+
+    import torch
+
+    rng = np.random.default_rng(77)
+    deltas = np.array([s * 10.0 ** -p for p in (15, 13, 11, 9, 7, 6, 5, 4, 3, 2, 1) for s in (-1, 1)] + [-0.3, 0.3, 0.0])
+    n_lam = 96
+    E = n_lam * len(deltas)
+    g, o = make_pair(n_envs=E, n_agents=1, grid=32, max_steps=8, seed=5, fixed_scenario=1)
+    # the agent sits under the top wall and pushes UP: it never moves, so lambda is the same every step
+    dist = rng.integers(1, 12, size=n_lam)
+    src = np.stack([np.full(n_lam, 16), 31 - dist], 1).repeat(len(deltas), 0)
+    start = np.tile(np.array([[16, 31]]), (E, 1)).reshape(E, 1, 2)
+    kw = dict(src_xy=src, src_int=(10 ** rng.uniform(5.5, 7.5, n_lam)).repeat(len(deltas)),
+              bkg=rng.uniform(10, 51, n_lam).repeat(len(deltas)), start_xy=start, n_poly=np.zeros(E, np.int32))
+    g.set_scenario(**kw); o.set_scenario(**kw)
+    g.reset(); o.reset()
+    up = np.ones((E, 1), np.int32)
+    g.step(torch.as_tensor(up, device=g.device)); o.step(up, maps=False)
+    lam = g.buffer("LAST_LAMBDA").cpu().numpy()[:, 0]
+    assert np.array_equal(lam, o.export("LAST_LAMBDA")[:, 0]) and (lam >= 10).all()
+
+    u = np.zeros((E, 1, 8))
+    k_tail = np.zeros(E, np.int64)
+    for e in range(E):
+        L = float(lam[e])
+        slam, loglam = math.sqrt(L), math.log(L)
+        b = 0.931 + 2.53 * slam
+        a = -0.059 + 0.02483 * b
+        invalpha = 1.1239 + 1.1328 / (b - 3.4)
+        usel = 0.5 + (0.44 + 0.05 * ((e // len(deltas)) % 7) / 7.0) * (1 if e % 2 else -1)  # us in (0.01, 0.06]: no fast accept
+        U = usel - 0.5
+        us = 0.5 - abs(U)
+        k = math.floor((2 * a / us + b) * U + L + 0.43)
+        k_tail[e] = k
+        if k < 0:  # rejected before the acceptance test: nothing to aim at
+            u[e, 0, :4] = [usel, 0.5, 0.5, 0.0]
+            continue
+        rhs = -L + k * loglam - math.lgamma(k + 1.0)
+        vstar = math.exp(rhs - math.log(invalpha) + math.log(a / (us * us) + b))
+        V = min(max(vstar * (1.0 + deltas[e % len(deltas)]), 0.0), 1.0 - 2.0 ** -53)
+        if us < 0.013:
+            V = min(V, us)  # stay clear of the early rejection (us < 0.013 and V > us)
+        # pair 1 = the adversarial draw; pair 2 accepts at once (us = 0.5, V = 0) with k = floor(lam + 0.43)
+        u[e, 0, :4] = [usel, V, 0.5, 0.0]
+    g.inject_uniforms(u); o.inject_uniforms(u)
+    g.step(torch.as_tensor(up, device=g.device)); o.step(up, maps=False)
+    cnt = g.buffer("LAST_COUNT").cpu().numpy()[:, 0]
+    want = o.export("LAST_COUNT")[:, 0]
+    assert np.array_equal(cnt, want), np.argwhere(cnt != want)[:8]
+    valid = k_tail >= 0
+    accepted = (cnt == k_tail) & valid
+    fallback = (cnt == np.floor(lam + 0.43)) & valid & ~accepted
+    assert accepted.sum() > E // 4 and fallback.sum() > E // 4, (accepted.sum(), fallback.sum())
+    assert g.errors() == o.errors() == 0
+    g.inject_uniforms(None)
