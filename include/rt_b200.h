@@ -119,11 +119,13 @@ typedef enum rt_buf {
                             and the dense VISIT / INTENSITY views are brought up to date by each
                             rt_env_buffer(VISIT or INTENSITY) call (which synchronises the device);
                             with the dense rasterisers they are live */
-  RT_BUF_CELLREC = 12,   /* uint16 [E][G*G][4] per-cell record of the step kernel: visits, smallest log
-                            entry of the cell + 1 (list head, 0 = none), record index in VREC + 1
+  RT_BUF_CELLREC = 12,   /* uint16 [E][G*G][4] per-cell record of the step kernel: visits, first bucket
+                            of the cell in LOG + 1 (0 = none), record index in VREC + 1
                             (0 = not visited this episode), unused                          */
-  RT_BUF_LOG = 13,       /* uint32 [T*A][E][2] reading log, time-major: {count, next larger
-                            entry of the same cell + 1}; entry index = tick*A + agent      */
+  RT_BUF_LOG = 13,       /* uint32 [T*A][E][8] reading buckets, time-major: 7 Poisson counts of ONE cell in
+                            ascending order (the first min(7, rest) are valid) + next bucket of the cell + 1;
+                            all buckets of a cell are full except the last and ordered by value; a bucket's
+                            id is tick*A + agent of the visit that opened it                  */
   RT_BUF__RESERVED14 = 14,
   RT_BUF_WELFORD = 15,   /* double [E][6]   mean, M2, var, std, zmax, zmin */
   RT_BUF_WELFORD_N = 16, /* int32  [E]      count                          */

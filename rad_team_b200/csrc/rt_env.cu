@@ -292,7 +292,7 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
       /*AGENT_XY*/ E * A * 8,   /*PREV_DIST*/ E * A * 4, /*START_XY*/ E * A * 8, /*SRC_XY*/ E * 8,
       /*SRC_INT*/ E * 8,        /*BKG*/ E * 8,           /*N_POLY*/ E * 4,       /*EDGES*/ E * RT_MAX_EDGES * 16,
       /*TICK*/ E * 4,           /*EPISODE*/ E * 4,       /*VISIT*/ E * cells * 2, /*INTENSITY*/ E * cells * 4,
-      /*CELLREC*/ E * cells * 8,   /*LOG*/ (size_t)cap * E * 8, /*unused*/ 0,       /*WELFORD*/ E * 48,
+      /*CELLREC*/ E * cells * 8,   /*LOG*/ (size_t)cap * E * 32, /*unused*/ 0,       /*WELFORD*/ E * 48,
       /*WELFORD_N*/ E * 4,      /*EST_MAXMIN*/ E * 16,   /*FLAGS*/ E * 4,        /*LAST_COUNT*/ E * A * 4,
       /*LAST_LOS*/ E * A,       /*LAST_LAMBDA*/ E * A * 8, /*LAST_EST*/ E * A * 8, /*LAST_Z*/ E * A * 8,
       /*LAST_VALUE*/ E * A * 8, /*VISIT_LUT*/ ((size_t)cap + 1) * 4, /*EP_RETURN*/ E * A * 4,
@@ -356,7 +356,7 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
   d.visit = (uint16_t*)h->buf_ptr[RT_BUF_VISIT];
   d.inten = (float*)h->buf_ptr[RT_BUF_INTENSITY];
   d.cellrec = (uint16_t*)h->buf_ptr[RT_BUF_CELLREC];
-  d.log = (uint2*)h->buf_ptr[RT_BUF_LOG];
+  d.log = (uint4*)h->buf_ptr[RT_BUF_LOG];
   d.welford = (double*)h->buf_ptr[RT_BUF_WELFORD];
   d.welford_n = (int32_t*)h->buf_ptr[RT_BUF_WELFORD_N];
   d.est_mm = (double*)h->buf_ptr[RT_BUF_EST_MAXMIN];

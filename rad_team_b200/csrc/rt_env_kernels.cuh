@@ -11,7 +11,7 @@
 //   k_reset_state, k_zero_maps   K5  masked episode reset + scenario generation.
 //
 // HBM layout is structure-of-arrays over envs so that neighbouring threads touch neighbouring addresses;
-// the reading log is time-major [T*A][E] for the same reason.
+// the pool of reading buckets is time-major [T*A][E] for the same reason.
 #pragma once
 #include <math_constants.h>
 
@@ -38,14 +38,15 @@ struct EnvDev {
   uint16_t* visit;  // [E][cells]  dense visit counts: live only when live_dense, else materialised on request
   float* inten;     // [E][cells]  dense intensity map: likewise
   uint16_t* cellrec;  // [E][cells][4]  k_step's random-access state of a cell, ONE 8-byte record per cell so that a
-                      //   visit costs one DRAM sector instead of three: [0] visits, [1] smallest log entry of the
-                      //   cell + 1 (list head, 0 = empty), [2] record index in vrec + 1 (0 = not visited), [3] unused
+                      //   visit costs one DRAM sector instead of three: [0] visits, [1] first bucket of the
+                      //   cell + 1 (chain head, 0 = empty), [2] record index in vrec + 1 (0 = not visited), [3] unused
   uint2* vrec;      // [E][rec_stride]  compact list of the VISITED cells, what the sparse rasteriser reads:
                     //   [0] = {n_visited, 0}; [1..2] = the agents' cells, 8 x uint16 (0xFFFF = none);
                     //   [2 + k] = {cell | visits << 16, fp32 bits of the intensity value}, k = 1..n_visited
   int rec_stride;   // uint2 per env (even)
   int rec_prefix;   // uint2 per env moved by the rasteriser's bulk copy (<= rec_stride, even)
-  uint2* log;       // [cap][E]    {count, next larger entry of the same cell + 1}
+  uint4* log;       // [cap][E][2] bucket pool, time-major: a bucket = 7 readings of ONE cell in ascending order +
+                    //   id (+1) of the cell's next bucket; bucket id = tick * A + agent of the visit that opened it
   double* welford;  // [E][6]
   int32_t* welford_n;
   double* est_mm;  // [E][2]
@@ -138,38 +139,83 @@ __host__ __device__ inline size_t step_smem_bytes(int epb, int A) {
 }
 
 // a9: IntensityResamplingEstimator.update + get_estimate (estimator.py:31-48,61-70) for one cell.
-// The cell's readings form a linked list sorted by value (head = smallest; log entry = {count, next+1});
-// insert reading `cnt` as entry `idx` and pick the median — elements (n-1)/2 and n/2 of the NEW list of
-// n readings — in the same walk.  `cur` = list head (+1, 0 = empty); (nd, have) = an already loaded head.
-__device__ __forceinline__ double list_insert_median(uint2* __restrict__ log, size_t E, uint16_t* head_cell,
-                                                     int idx, int cnt, int n, int cur, uint2 nd, bool have) {
+// The cell's readings live in a chain of 32-byte BUCKETS — seven values in ascending order and the id (+1) of
+// the next bucket; every bucket of a chain is full except the last, and all values of a bucket are <= those
+// of the next.  One DRAM sector therefore holds the whole history of a cell visited up to seven times and a
+// visit costs ceil(n / 7) dependent loads (the previous structure, a value-sorted linked list with one reading
+// per node, needed ~n / 2).  Inserting reading `cnt` bubbles it into its bucket, cascades the evicted maximum
+// down the chain, and picks the median — elements (n-1)/2 and n/2 of the NEW sequence of n readings — on the
+// way.  A chain that needs one more bucket takes slot `idx` = tick * A + agent of the time-major pool, so no
+// allocator state exists and a reset has nothing to clear.  `cur` = first bucket (+1, 0 = none).
+__device__ __forceinline__ double bucket_insert_median(uint4* __restrict__ pool, size_t E, uint16_t* head_cell,
+                                                       int idx, uint32_t cnt, int n, int cur) {
+  if (cur == 0) {  // first reading of this cell
+    uint4* np = pool + (size_t)idx * E * 2;
+    np[0] = make_uint4(cnt, 0u, 0u, 0u);
+    np[1] = make_uint4(0u, 0u, 0u, 0u);
+    *head_cell = (uint16_t)(idx + 1);
+    return (double)cnt;
+  }
   const int k1 = (n - 1) >> 1, k2 = n >> 1;
-  int pred = 0, m1 = 0, m2 = 0;
-  bool inserted = false;
-  // a well-formed list ends within n steps; the bound only protects against a corrupted (cyclic) list
-  // restored through rt_env_buffer — a kernel must never spin forever
-  for (int i = 0; (i <= k2 || !inserted) && i <= n + 1; ++i) {
-    if (cur != 0 && !have) {
-      nd = log[(size_t)(cur - 1) * E];
-      have = true;
+  uint32_t m1 = 0u, m2 = 0u, carry = cnt;
+  bool pending = true;
+  int base = 0;          // index, in the new sequence, of the first element of the current bucket
+  int left = n - 1;      // old readings not yet passed
+  // a well-formed chain has ceil((n - 1) / 7) buckets; the bound only protects against a corrupted (cyclic)
+  // chain restored through rt_env_buffer — a kernel must never spin forever
+  const int max_hops = (n + 5) / 7 + 1;
+  for (int hop = 0; hop < max_hops; ++hop) {
+    uint4* bp = pool + (size_t)(cur - 1) * E * 2;
+    const uint4 p_lo = bp[0], p_hi = bp[1];
+    uint32_t v[7] = {p_lo.x, p_lo.y, p_lo.z, p_lo.w, p_hi.x, p_hi.y, p_hi.z};
+    uint32_t next = p_hi.w;
+    const int m = left < 7 ? left : 7;  // valid entries of this bucket before the insertion
+    left -= m;
+    int m_new = m;
+    bool dirty = false;
+    if (pending && (m < 7 || carry < v[6])) {
+      uint32_t x = carry;  // bubble pass: v[0..m-1] keep the m smallest of {v, carry}, x leaves with the largest
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        const bool sw = i < m && v[i] > x;
+        const uint32_t t = v[i];
+        v[i] = sw ? x : t;
+        x = sw ? t : x;
+      }
+      if (m < 7) {  // room left (this is the last bucket): the largest takes the free place
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+          if (i == m) v[i] = x;
+        m_new = m + 1;
+        pending = false;
+      } else {
+        carry = x;  // evicted maximum moves on
+      }
+      dirty = true;
     }
-    int elem;
-    if (!inserted && (cur == 0 || (int)nd.x > cnt)) {
-      elem = cnt;
-      inserted = true;
-      log[(size_t)idx * E] = make_uint2((uint32_t)cnt, (uint32_t)cur);
-      if (pred == 0)
-        *head_cell = (uint16_t)(idx + 1);
-      else
-        log[(size_t)(pred - 1) * E].y = (uint32_t)(idx + 1);
-    } else {
-      elem = (int)nd.x;
-      pred = cur;
-      cur = (int)nd.y;
-      have = false;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      if (i < m_new && base + i == k1) m1 = v[i];
+      if (i < m_new && base + i == k2) m2 = v[i];
     }
-    if (i == k1) m1 = elem;
-    if (i == k2) m2 = elem;
+    base += m_new;
+    if (next == 0u && pending) {  // the chain grows by one bucket holding the carried maximum
+      uint4* np = pool + (size_t)idx * E * 2;
+      np[0] = make_uint4(carry, 0u, 0u, 0u);
+      np[1] = make_uint4(0u, 0u, 0u, 0u);
+      if (base == k1) m1 = carry;
+      if (base == k2) m2 = carry;
+      next = (uint32_t)(idx + 1);
+      pending = false;
+      dirty = true;
+      left = -1;  // finished
+    }
+    if (dirty) {
+      bp[0] = make_uint4(v[0], v[1], v[2], v[3]);
+      bp[1] = make_uint4(v[4], v[5], v[6], next);
+    }
+    if (left < 0 || next == 0u || (!pending && base > k2)) break;
+    cur = (int)next;
   }
   // statistics.median: middle element, or the mean of the middle two
   return (n & 1) ? (double)m2 : __ddiv_rn((double)((long long)m1 + (long long)m2), 2.0);
@@ -178,7 +224,7 @@ __device__ __forceinline__ double list_insert_median(uint2* __restrict__ log, si
 // K4a: the env's agents feed ONE Welford standardiser / normaliser, in agent order (one thread per env).
 // The per-cell estimator work was already done in parallel by the agents' own threads, except for agents
 // whose cell was also entered by an earlier agent of the env in this very step (nread == 0): those are
-// replayed here, in order, against the updated list.
+// replayed here, in order, against the updated bucket chain.
 __device__ __forceinline__ void stats_chain(const EnvDev& d, const StepSmem& s, int e, int le, int tick,
                                             WelfordState& w, double emx, double emn, int nv) {
   const int A = d.A;
@@ -200,8 +246,8 @@ __device__ __forceinline__ void stats_chain(const EnvDev& d, const StepSmem& s, 
       n = (int)(cr.x & 0xffffu) + 1;
       crec[4 * cell] = (uint16_t)n;
       if (d.live_dense) visit[cell] = (uint16_t)n;
-      est = list_insert_median(d.log + e, (size_t)d.E, crec + 4 * cell + 1, tick * A + aa, s.count[i], n,
-                               (int)(cr.x >> 16), make_uint2(0u, 0u), false);
+      est = bucket_insert_median(d.log + 2 * (size_t)e, (size_t)d.E, crec + 4 * cell + 1, tick * A + aa,
+                                 (uint32_t)s.count[i], n, (int)(cr.x >> 16));
       sl = (int)(cr.y & 0xffffu);
     }
     if (sl == 0) {  // first visit of this cell in the episode: open a record
@@ -311,7 +357,7 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
   }
 
   // Per-env statistics are owned by the FIRST n_valid threads of the CTA (thread i <-> env e0 + i): the
-  // sequential chain at the end is pure arithmetic + stores (the list walks happen in the agents' own
+  // sequential chain at the end is pure arithmetic + stores (the bucket walks happen in the agents' own
   // threads), so it runs best in fully populated warps.  Start the owners' loads now.
   WelfordState w;
   double emx = 0.0, emn = 0.0, src_int = 0.0, bkg = 0.0;
@@ -403,8 +449,9 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
     for (int i = 0; i < nb; ++i) strength = __dmul_rn(strength, d.transmission);
     const double lam = __dadd_rn(__ddiv_rn(strength, d2), bkg);
 
-    uint2 pnode = make_uint2(0u, 0u);
-    if (!clash && ph != 0u) pnode = d.log[(size_t)(ph - 1) * d.E + e];
+    // pull the cell's first bucket towards the L2 while the sampler computes.  (Loading it into registers here
+    // costs spills across the sampler: 0.0507 vs 0.0487 ms, profiles/r03d.)
+    if (!clash && ph != 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.log + ((size_t)(ph - 1) * d.E + e) * 2));
 
     // N3: Poisson count
     Draws dr;
@@ -425,8 +472,8 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
       uint16_t* cr16 = d.cellrec + ((size_t)e * d.cells + cell) * 4;
       cr16[0] = (uint16_t)n;
       if (d.live_dense) d.visit[(size_t)e * d.cells + cell] = (uint16_t)n;
-      est = list_insert_median(d.log + e, (size_t)d.E, cr16 + 1, tick * A + a, (int)cnt,
-                               n, (int)ph, pnode, ph != 0u);
+      est = bucket_insert_median(d.log + 2 * (size_t)e, (size_t)d.E, cr16 + 1, tick * A + a, (uint32_t)cnt, n,
+                                 (int)ph);
     }
     s.count[t] = (int)cnt;
     s.slot[t] = (int)psl;

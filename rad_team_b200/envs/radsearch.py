@@ -65,7 +65,7 @@ _BUF_SPEC = {
     "VISIT": ("uint16", lambda E, A, c, cap: (E, c)),
     "INTENSITY": ("float32", lambda E, A, c, cap: (E, c)),
     "CELLREC": ("uint16", lambda E, A, c, cap: (E, c, 4)),
-    "LOG": ("int32", lambda E, A, c, cap: (cap, E, 2)),
+    "LOG": ("int32", lambda E, A, c, cap: (cap, E, 8)),
     "WELFORD": ("float64", lambda E, A, c, cap: (E, 6)),
     "WELFORD_N": ("int32", lambda E, A, c, cap: (E,)),
     "EST_MAXMIN": ("float64", lambda E, A, c, cap: (E, 2)),
