@@ -119,13 +119,14 @@ typedef enum rt_buf {
                             and the dense VISIT / INTENSITY views are brought up to date by each
                             rt_env_buffer(VISIT or INTENSITY) call (which synchronises the device);
                             with the dense rasterisers they are live */
-  RT_BUF_CELLREC = 12,   /* uint16 [E][G*G][4] per-cell record of the step kernel: visits, first bucket
+  RT_BUF_CELLREC = 12,   /* uint16 [E][G*G][4] per-cell record of the step kernel: unused, first bucket
                             of the cell in LOG + 1 (0 = none), record index in VREC + 1
                             (0 = not visited this episode), unused                          */
   RT_BUF_LOG = 13,       /* uint32 [T*A][E][8] reading buckets, time-major: 7 Poisson counts of ONE cell in
-                            ascending order (the first min(7, rest) are valid) + next bucket of the cell + 1;
-                            all buckets of a cell are full except the last and ordered by value; a bucket's
-                            id is tick*A + agent of the visit that opened it                  */
+                            ascending order (the first min(7, rest) are valid) + a link word: low 16 bits =
+                            next bucket of the cell + 1, high 16 bits (first bucket of a cell only) = number
+                            of readings of the cell; all buckets of a cell are full except the last and
+                            ordered by value; a bucket's id is tick*A + agent of the visit that opened it */
   RT_BUF__RESERVED14 = 14,
   RT_BUF_WELFORD = 15,   /* double [E][6]   mean, M2, var, std, zmax, zmin */
   RT_BUF_WELFORD_N = 16, /* int32  [E]      count                          */

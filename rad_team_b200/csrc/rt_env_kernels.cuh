@@ -38,15 +38,17 @@ struct EnvDev {
   uint16_t* visit;  // [E][cells]  dense visit counts: live only when live_dense, else materialised on request
   float* inten;     // [E][cells]  dense intensity map: likewise
   uint16_t* cellrec;  // [E][cells][4]  k_step's random-access state of a cell, ONE 8-byte record per cell so that a
-                      //   visit costs one DRAM sector instead of three: [0] visits, [1] first bucket of the
-                      //   cell + 1 (chain head, 0 = empty), [2] record index in vrec + 1 (0 = not visited), [3] unused
+                      //   visit reads one DRAM sector (and a revisit writes none): [0] unused (the visit count
+                      //   travels with the cell's first bucket), [1] first bucket of the cell + 1 (0 = none),
+                      //   [2] record index in vrec + 1 (0 = not visited), [3] unused
   uint2* vrec;      // [E][rec_stride]  compact list of the VISITED cells, what the sparse rasteriser reads:
                     //   [0] = {n_visited, 0}; [1..2] = the agents' cells, 8 x uint16 (0xFFFF = none);
                     //   [2 + k] = {cell | visits << 16, fp32 bits of the intensity value}, k = 1..n_visited
   int rec_stride;   // uint2 per env (even)
   int rec_prefix;   // uint2 per env moved by the rasteriser's bulk copy (<= rec_stride, even)
   uint4* log;       // [cap][E][2] bucket pool, time-major: a bucket = 7 readings of ONE cell in ascending order +
-                    //   id (+1) of the cell's next bucket; bucket id = tick * A + agent of the visit that opened it
+                    //   link word (low half: id + 1 of the cell's next bucket; high half, first bucket only: readings
+                    //   of the cell); bucket id = tick * A + agent of the visit that opened it
   double* welford;  // [E][6]
   int32_t* welford_n;
   double* est_mm;  // [E][2]
@@ -139,23 +141,31 @@ __host__ __device__ inline size_t step_smem_bytes(int epb, int A) {
 }
 
 // a9: IntensityResamplingEstimator.update + get_estimate (estimator.py:31-48,61-70) for one cell.
-// The cell's readings live in a chain of 32-byte BUCKETS — seven values in ascending order and the id (+1) of
-// the next bucket; every bucket of a chain is full except the last, and all values of a bucket are <= those
-// of the next.  One DRAM sector therefore holds the whole history of a cell visited up to seven times and a
-// visit costs ceil(n / 7) dependent loads (the previous structure, a value-sorted linked list with one reading
-// per node, needed ~n / 2).  Inserting reading `cnt` bubbles it into its bucket, cascades the evicted maximum
-// down the chain, and picks the median — elements (n-1)/2 and n/2 of the NEW sequence of n readings — on the
-// way.  A chain that needs one more bucket takes slot `idx` = tick * A + agent of the time-major pool, so no
-// allocator state exists and a reset has nothing to clear.  `cur` = first bucket (+1, 0 = none).
+// The cell's readings live in a chain of 32-byte BUCKETS — seven values in ascending order and a link word:
+// id (+1) of the next bucket in the low half and, in the chain's FIRST bucket, the number of readings of the
+// cell in the high half.  Every bucket of a chain is full except the last, and all values of a bucket are <=
+// those of the next.  One DRAM sector therefore holds the whole history of a cell visited up to seven times and
+// a visit costs ceil(n / 7) dependent loads (the previous structure, a value-sorted linked list with one
+// reading per node, needed ~n / 2); because the visit count travels with the bucket, a revisit leaves the cell
+// record untouched — one scattered dirty sector less per agent-step.  Inserting reading `cnt` bubbles it into
+// its bucket, cascades the evicted maximum down the chain, and picks the median — elements (n-1)/2 and n/2 of
+// the NEW sequence of n readings — on the way.  A chain that needs one more bucket takes slot `idx` = tick * A +
+// agent of the time-major pool, so no allocator state exists and a reset has nothing to clear.
+// `cur` = first bucket (+1, 0 = none); returns the median and, in n_out, the new number of readings.
 __device__ __forceinline__ double bucket_insert_median(uint4* __restrict__ pool, size_t E, uint16_t* head_cell,
-                                                       int idx, uint32_t cnt, int n, int cur) {
+                                                       int idx, uint32_t cnt, int cur, int& n_out) {
   if (cur == 0) {  // first reading of this cell
     uint4* np = pool + (size_t)idx * E * 2;
     np[0] = make_uint4(cnt, 0u, 0u, 0u);
-    np[1] = make_uint4(0u, 0u, 0u, 0u);
+    np[1] = make_uint4(0u, 0u, 0u, 1u << 16);
     *head_cell = (uint16_t)(idx + 1);
+    n_out = 1;
     return (double)cnt;
   }
+  uint4* bp = pool + (size_t)(cur - 1) * E * 2;
+  uint4 p_lo = bp[0], p_hi = bp[1];
+  const int n = (int)(p_hi.w >> 16) + 1;
+  n_out = n;
   const int k1 = (n - 1) >> 1, k2 = n >> 1;
   uint32_t m1 = 0u, m2 = 0u, carry = cnt;
   bool pending = true;
@@ -165,14 +175,13 @@ __device__ __forceinline__ double bucket_insert_median(uint4* __restrict__ pool,
   // chain restored through rt_env_buffer — a kernel must never spin forever
   const int max_hops = (n + 5) / 7 + 1;
   for (int hop = 0; hop < max_hops; ++hop) {
-    uint4* bp = pool + (size_t)(cur - 1) * E * 2;
-    const uint4 p_lo = bp[0], p_hi = bp[1];
     uint32_t v[7] = {p_lo.x, p_lo.y, p_lo.z, p_lo.w, p_hi.x, p_hi.y, p_hi.z};
-    uint32_t next = p_hi.w;
+    uint32_t next = p_hi.w & 0xffffu;
+    const uint32_t count_word = hop == 0 ? (uint32_t)n << 16 : 0u;
     const int m = left < 7 ? left : 7;  // valid entries of this bucket before the insertion
     left -= m;
     int m_new = m;
-    bool dirty = false;
+    bool dirty = hop == 0;  // the first bucket carries the count
     if (pending && (m < 7 || carry < v[6])) {
       uint32_t x = carry;  // bubble pass: v[0..m-1] keep the m smallest of {v, carry}, x leaves with the largest
 #pragma unroll
@@ -212,10 +221,12 @@ __device__ __forceinline__ double bucket_insert_median(uint4* __restrict__ pool,
     }
     if (dirty) {
       bp[0] = make_uint4(v[0], v[1], v[2], v[3]);
-      bp[1] = make_uint4(v[4], v[5], v[6], next);
+      bp[1] = make_uint4(v[4], v[5], v[6], next | count_word);
     }
     if (left < 0 || next == 0u || (!pending && base > k2)) break;
-    cur = (int)next;
+    bp = pool + (size_t)(next - 1) * E * 2;
+    p_lo = bp[0];
+    p_hi = bp[1];
   }
   // statistics.median: middle element, or the mean of the middle two
   return (n & 1) ? (double)m2 : __ddiv_rn((double)((long long)m1 + (long long)m2), 2.0);
@@ -243,11 +254,9 @@ __device__ __forceinline__ void stats_chain(const EnvDev& d, const StepSmem& s, 
       sl = s.slot[i];
     } else {
       const uint2 cr = *reinterpret_cast<const uint2*>(crec + 4 * cell);
-      n = (int)(cr.x & 0xffffu) + 1;
-      crec[4 * cell] = (uint16_t)n;
-      if (d.live_dense) visit[cell] = (uint16_t)n;
       est = bucket_insert_median(d.log + 2 * (size_t)e, (size_t)d.E, crec + 4 * cell + 1, tick * A + aa,
-                                 (uint32_t)s.count[i], n, (int)(cr.x >> 16));
+                                 (uint32_t)s.count[i], (int)(cr.x >> 16), n);
+      if (d.live_dense) visit[cell] = (uint16_t)n;
       sl = (int)(cr.y & 0xffffu);
     }
     if (sl == 0) {  // first visit of this cell in the episode: open a record
@@ -390,7 +399,7 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
   const size_t ia = (size_t)e * A + a;
   const float4* my_edges = s.edges + (size_t)le * kEdgeRowF4;
   int nx = pos.x, ny = pos.y, cell = 0;
-  unsigned pv = 0u, ph = 0u, psl = 0u;
+  unsigned ph = 0u, psl = 0u;
   if (valid) {
     if (skip) {  // reference raises before touching state: report the unchanged position
       reinterpret_cast<int2*>(obs_xy)[ia] = pos;
@@ -426,8 +435,7 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
     s.cell[t] = cell;
     if (live) {  // cell state for the estimator: the loads fly while line of sight and sampler compute
       const size_t mcell = (size_t)e * d.cells + cell;
-      const uint2 cr = reinterpret_cast<const uint2*>(d.cellrec)[mcell];  // visits | head << 16, slot
-      pv = cr.x & 0xffffu;
+      const uint2 cr = reinterpret_cast<const uint2*>(d.cellrec)[mcell];  // first bucket << 16, slot
       ph = cr.x >> 16;
       psl = cr.y & 0xffffu;
     }
@@ -468,12 +476,10 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
     int n = 0;
     double est = 0.0;
     if (!clash) {
-      n = (int)pv + 1;
       uint16_t* cr16 = d.cellrec + ((size_t)e * d.cells + cell) * 4;
-      cr16[0] = (uint16_t)n;
+      est = bucket_insert_median(d.log + 2 * (size_t)e, (size_t)d.E, cr16 + 1, tick * A + a, (uint32_t)cnt, (int)ph,
+                                 n);
       if (d.live_dense) d.visit[(size_t)e * d.cells + cell] = (uint16_t)n;
-      est = bucket_insert_median(d.log + 2 * (size_t)e, (size_t)d.E, cr16 + 1, tick * A + a, (uint32_t)cnt, n,
-                                 (int)ph);
     }
     s.count[t] = (int)cnt;
     s.slot[t] = (int)psl;
