@@ -275,7 +275,9 @@ __device__ __forceinline__ void stats_chain(const EnvDev& d, const StepSmem& s, 
     // one scattered 4-byte store per agent-step is worth ~10 % of this kernel (sensitivity probe):
     // the sparse rasterisers read the record below, so the dense map is only kept current when something reads it
     if (d.live_dense) inten[cell] = (float)val;
-    rec[2 + sl] = make_uint2((uint32_t)cell | ((uint32_t)n << 16), __float_as_uint((float)val));
+    // (n <= cap in any state this library produced; the clamp keeps the rasteriser's table lookup in bounds for a
+    // garbage state restored through rt_env_buffer)
+    rec[2 + sl] = make_uint2((uint32_t)cell | ((uint32_t)min(n, d.cap) << 16), __float_as_uint((float)val));
     const size_t ia = (size_t)e * A + aa;
     d.last_est[ia] = est;
     d.last_z[ia] = z;

@@ -557,3 +557,25 @@ def test_ptrs_acceptance_threshold_adversarial():
     assert accepted.sum() > E // 4 and fallback.sum() > E // 4, (accepted.sum(), fallback.sum())
     assert g.errors() == o.errors() == 0
     g.inject_uniforms(None)
+
+
+@pytest.mark.timeout(120)
+def test_corrupted_bucket_chain_cannot_hang_the_kernel():
+    """A state restored through rt_env_buffer may be garbage; the bucket walk is bounded by the count it reads,
+    so a cyclic chain with the largest possible count costs a few thousand hops, not an endless loop."""
+    import torch
+    from rad_team_b200.envs import BatchedRadSearchEnv
+
+    g = BatchedRadSearchEnv(n_envs=64, n_agents=2, grid=2, max_steps=400, seed=3, poly_min=0, poly_max=0)
+    g.reset()
+    act = torch.ones((64, 2), dtype=torch.int32, device=g.device)
+    for _ in range(20):
+        g.step(act)
+    log = g.buffer("LOG")                                   # int32 [cap, E, 8]
+    ids = torch.arange(1, log.shape[0] + 1, dtype=torch.int32, device=g.device).view(-1, 1)
+    log[:, :, 7] = ids | (0x7FFF << 16)                     # every bucket links to itself and claims 32,767 readings
+    for _ in range(3):
+        g.step(act)
+    torch.cuda.synchronize()
+    assert g.errors() & ~0x1F == 0
+    g.close()
