@@ -2,8 +2,9 @@
 
 The reference keys a dict by arbitrary (x, y) tuples; the device structure has a fixed number of key
 slots, so the facade maps each new key to the next free slot (host dict) and the kernels keep, per slot,
-a value-sorted linked list of readings (median = walk to the middle) — the same structure the env step
-kernel uses per map cell."""
+a value-sorted linked list of readings (median = walk to the middle).  (The env step kernel keeps its per-cell
+readings in 32-byte sorted bucket chains instead — rt_env_kernels.cuh: bucket_insert_median; this stand-alone
+object is a parity surface for the reference's class, not a hot path.)"""
 from __future__ import annotations
 
 import ctypes as C
