@@ -87,6 +87,22 @@ struct Draws {
     const uint64_t bits = ((uint64_t)hi << 32) | lo;
     return __dmul_rn((double)(bits >> 11), 1.0 / 9007199254740992.0);
   }
+
+  // Two consecutive draws.  From an even position of the Philox sequence they are the two halves of ONE block:
+  // a straight-line path without the block cache (PTRS consumes its uniforms in exactly such pairs); any other
+  // case — injected table, odd position — goes through next().  Same values either way.
+  __device__ __forceinline__ void next_pair(double& u0, double& u1) {
+    if (inj == nullptr && (k & 1) == 0) {
+      uint32_t w[4];
+      ph.block((uint32_t)(k >> 1), w);
+      k += 2;
+      u0 = __dmul_rn((double)((((uint64_t)w[1] << 32) | w[0]) >> 11), 1.0 / 9007199254740992.0);
+      u1 = __dmul_rn((double)((((uint64_t)w[3] << 32) | w[2]) >> 11), 1.0 / 9007199254740992.0);
+    } else {
+      u0 = next();
+      u1 = next();
+    }
+  }
 };
 
 // ---------------------------------------------------------------------------
@@ -290,9 +306,10 @@ __device__ __forceinline__ long long poisson_draw(double lam, Draws& d, int& fla
   const double vr = __dsub_rn(0.9277, __ddiv_rn(3.6224, __dsub_rn(b, 2.0)));
   long long k = 0;
   for (int it = 0; it < kPoissonMaxIters; ++it) {
-    const double U = __dsub_rn(d.next(), 0.5);
-    const double V = d.next();
+    double u0, V;
+    d.next_pair(u0, V);
     if (d.overflow) break;
+    const double U = __dsub_rn(u0, 0.5);
     const double us = __dsub_rn(0.5, fabs(U));
     // floor((2*a/us + b)*U + lam + 0.43)
     const double t = __dadd_rn(__ddiv_rn(__dmul_rn(2.0, a), us), b);
