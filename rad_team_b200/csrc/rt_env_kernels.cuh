@@ -123,9 +123,27 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // CTA.  blockDim.x = envs_per_cta * A.
 constexpr int kEdgeRowF4 = RT_MAX_EDGES + 1;  // 21 float4 = 336 B rows: conflict-free float4 reads
 
+// Per-env state of the sequential chain, staged global -> shared by cp.async at the top of the CTA so that it
+// occupies no registers while the per-agent phases run (it used to: 19 registers held across the sampler, the
+// point of highest pressure).  Layout of one 96-byte row: [0..47] Welford mean, M2, var, std, zmax, zmin;
+// [48..63] estimator max, min; [64..71] record header slot 0 {n_visited, 0}; [72] Welford count; [76] tick.
+constexpr int kOwnF4 = 6;
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 struct StepSmem {  // carved from dynamic shared memory, see step_smem_bytes()
   uint64_t* bar;
   float4* edges;   // [epb][kEdgeRowF4]
+  uint4* own;      // [epb][kOwnF4]  the env's sequential statistics, staged by cp.async (see OwnerState)
   double* est;     // [epb*A]  median estimate computed by the agent's own thread
   int* n_poly;     // [epb]
   int* skip;       // [epb]  RT_FLAG_* that void this env's step
@@ -136,8 +154,8 @@ struct StepSmem {  // carved from dynamic shared memory, see step_smem_bytes()
   int* nread;      // [epb*A]  readings at the cell incl. this one; 0 = deferred to the owner (cell clash)
 };
 __host__ __device__ inline size_t step_smem_bytes(int epb, int A) {
-  return 16 + (size_t)epb * kEdgeRowF4 * 16 + (size_t)epb * A * 8 + (size_t)epb * 3 * 4 +
-         (size_t)epb * A * 4 * 4;
+  return 16 + (size_t)epb * kEdgeRowF4 * 16 + (size_t)epb * kOwnF4 * 16 + (size_t)epb * A * 8 +
+         (size_t)epb * 3 * 4 + (size_t)epb * A * 4 * 4;
 }
 
 // a9: IntensityResamplingEstimator.update + get_estimate (estimator.py:31-48,61-70) for one cell.
@@ -316,7 +334,8 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
   StepSmem s;
   s.bar = reinterpret_cast<uint64_t*>(smem_raw);
   s.edges = reinterpret_cast<float4*>(smem_raw + 16);
-  s.est = reinterpret_cast<double*>(smem_raw + 16 + (size_t)epb * kEdgeRowF4 * 16);
+  s.own = reinterpret_cast<uint4*>(smem_raw + 16 + (size_t)epb * kEdgeRowF4 * 16);
+  s.est = reinterpret_cast<double*>(s.own + (size_t)epb * kOwnF4);
   s.n_poly = reinterpret_cast<int*>(s.est + epb * A);
   s.skip = s.n_poly + epb;
   s.eflags = s.skip + epb;
@@ -370,9 +389,8 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
   // Per-env statistics are owned by the FIRST n_valid threads of the CTA (thread i <-> env e0 + i): the
   // sequential chain at the end is pure arithmetic + stores (the bucket walks happen in the agents' own
   // threads), so it runs best in fully populated warps.  Start the owners' loads now.
-  WelfordState w;
-  double emx = 0.0, emn = 0.0, src_int = 0.0, bkg = 0.0;
-  int episode = 0, nv = 0, tick3 = 0;
+  double src_int = 0.0, bkg = 0.0;
+  int episode = 0;
   if (valid) {
     src_int = d.src_int[e];
     bkg = d.bkg[e];
@@ -381,15 +399,16 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
   const bool owner = t < n_valid;
   const int e3 = e0 + t;
   if (owner) {
-    const double2* wp = reinterpret_cast<const double2*>(d.welford + (size_t)e3 * 6);
-    const double2 w0 = wp[0], w1 = wp[1], w2 = wp[2];
-    w.mean = w0.x; w.m2 = w0.y; w.var = w1.x; w.sd = w1.y; w.zmax = w2.x; w.zmin = w2.y;
-    w.count = d.welford_n[e3];
-    const double2 mm = reinterpret_cast<const double2*>(d.est_mm)[e3];
-    emx = mm.x;
-    emn = mm.y;
-    nv = (int)d.vrec[(size_t)e3 * d.rec_stride].x;
-    tick3 = d.tick[e3];
+    unsigned char* row = reinterpret_cast<unsigned char*>(s.own + (size_t)t * kOwnF4);
+    const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(d.welford + (size_t)e3 * 6);
+    cp_async16(row, wsrc);
+    cp_async16(row + 16, wsrc + 16);
+    cp_async16(row + 32, wsrc + 32);
+    cp_async16(row + 48, d.est_mm + (size_t)e3 * 2);
+    cp_async8(row + 64, d.vrec + (size_t)e3 * d.rec_stride);
+    cp_async4(row + 72, d.welford_n + e3);
+    cp_async4(row + 76, d.tick + e3);
+    cp_async_commit();
   }
 
   mbar_wait(s.bar, 0);  // geometry of every env of this CTA has landed in shared memory
@@ -501,7 +520,15 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
       atomicOr(&d.flags[e3], skip3);
       atomicOr(d.step_flags, skip3);
     } else {
-      stats_chain(d, s, e3, t, tick3, w, emx, emn, nv);
+      cp_async_wait_all();  // this thread's own copies: its row of the staged state is complete
+      const unsigned char* row = reinterpret_cast<const unsigned char*>(s.own + (size_t)t * kOwnF4);
+      const double2 w0 = *reinterpret_cast<const double2*>(row), w1 = *reinterpret_cast<const double2*>(row + 16),
+                    w2 = *reinterpret_cast<const double2*>(row + 32), mm = *reinterpret_cast<const double2*>(row + 48);
+      WelfordState w;
+      w.mean = w0.x; w.m2 = w0.y; w.var = w1.x; w.sd = w1.y; w.zmax = w2.x; w.zmin = w2.y;
+      w.count = *reinterpret_cast<const int*>(row + 72);
+      stats_chain(d, s, e3, t, *reinterpret_cast<const int*>(row + 76), w, mm.x, mm.y,
+                  (int)*reinterpret_cast<const uint32_t*>(row + 64));
     }
   }
 }
