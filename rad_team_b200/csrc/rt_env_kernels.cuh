@@ -459,6 +459,10 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
       const uint2 cr = reinterpret_cast<const uint2*>(d.cellrec)[mcell];  // first bucket << 16, slot
       ph = cr.x >> 16;
       psl = cr.y & 0xffffu;
+      // The owner will write this cell's 8-byte visited-cell record at the end.  A partial write into a sector
+      // that is NOT in the L2 is dear for whoever reads it next (the rasteriser): fetch the sector now, the write
+      // then lands in a complete line (-1.6 % on the step, profiles/r03m).
+      if (psl != 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.vrec + (size_t)e * d.rec_stride + 2 + psl));
     }
   }
   __syncthreads();  // every agent's new cell is known to its env-mates
