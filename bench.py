@@ -137,6 +137,16 @@ def ncu_traffic_per_launch(n_envs):
     return None
 
 
+def ncu_kstep_alu():
+    """SM / ALU utilisation of k_step from the committed ncu --set full capture (profiles/kstep_alu.json): the
+    kernel that holds the line-of-sight tests is judged on instruction issue, not on HBM."""
+    p = REPO / "profiles" / "kstep_alu.json"
+    try:
+        return json.loads(p.read_text())
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_oracle_rate(w, n_envs, steps, warmup, threads, seconds=None):
     """Time the CPU oracle (all `threads` host threads) on `n_envs` envs of the workload.
@@ -443,7 +453,8 @@ def run_ours(args, rank, world, local_rank):
                                         + (" + NCCL all-gather/merge" if world > 1 else "") + " + reset, inside the timed region",
                        "arithmetic": "fp64 physics/statistics, fp32 geometry and maps, int32 indices/counts"},
             "roofline": roofline,
-            "kernels": {"step_ms": fused_ms, "k_step_ms": kstep_ms, "raster_ms": raster_ms},
+            "kernels": {"step_ms": fused_ms, "k_step_ms": kstep_ms, "raster_ms": raster_ms,
+                        "k_step_ncu": ncu_kstep_alu()},
             "normalisation_kernels": k4,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "agent-env-steps/s", "h2d_bytes_per_step": E * A * 4,
