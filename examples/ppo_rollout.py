@@ -4,6 +4,12 @@
 
     python examples/ppo_rollout.py [--envs 8192] [--agents 3] [--horizon 32] [--iters 3] [--dtype bf16]
     torchrun --nproc-per-node N examples/ppo_rollout.py ...      (envs are per GPU; grads all-reduced by DDP)
+    config 5 at scale (8 x B200, 131,072 envs per GPU = 1,048,576 envs):
+        torchrun --nproc-per-node 8 examples/ppo_rollout.py --envs 131072 --horizon 16 --chunk 32768 --minibatches 64
+
+The policy's forward pass walks the envs in chunks (`--chunk`), so its activations never exceed one chunk; the
+observation slots themselves ([horizon + 1, E, 3, 32, 32], compressible HBM) are the env's output tensors.
+NVTX ranges (`rt_env_step`, `policy`, `close_rollout`, `ppo_update`) make an nsys timeline readable.
 
 Every env step rasterises the observation straight into its slot of the rollout buffer
 (`env.step(actions, out_maps=obs[t])`): no copy between the env and the network's input tensor.
@@ -21,7 +27,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
-from rad_team_b200.distributed import merge_rollout_stats  # noqa: E402
+from rad_team_b200.distributed import RolloutStatsExchange  # noqa: E402
 from rad_team_b200.envs import BatchedRadSearchEnv  # noqa: E402
 from rad_team_b200.memory import obs_tensor, readings_tensor  # noqa: E402
 from rad_team_b200.math_utils import RunningMoments  # noqa: E402
@@ -58,6 +64,7 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--minibatches", type=int, default=4)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--chunk", type=int, default=0, help="envs per policy forward pass (0 = all at once)")
     args = ap.parse_args()
 
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -84,7 +91,17 @@ def main():
     dn = torch.empty((T, E, A), dtype=torch.uint8, device=dev)
     readings = readings_tensor((120, E, A), device=dev)
     env.set_rollout(readings)
-    moments = RunningMoments()
+    local_m, moments = RunningMoments(), RunningMoments()   # this rollout's readings / the global running normaliser
+    exchange = RolloutStatsExchange()                        # once per rollout: peer-memory kernel (NCCL as the fallback)
+    chunk = args.chunk if args.chunk > 0 else E
+    nvtx = torch.cuda.nvtx
+
+    def policy(maps, pos, reading):
+        """Forward pass in env chunks: activations of one chunk at a time."""
+        if chunk >= E:
+            return model(maps, pos, reading)
+        outs = [model(maps[i:i + chunk], pos[i:i + chunk], reading[i:i + chunk]) for i in range(0, E, chunk)]
+        return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     env_ms = policy_ms = update_ms = 0.0
@@ -97,31 +114,38 @@ def main():
         for t in range(T):
             a0, a1, a2 = ev(), ev(), ev()
             a0.record()
+            nvtx.range_push("policy")
             with torch.no_grad(), torch.autocast("cuda", dtype=amp, enabled=amp != torch.float32):
-                logits, v = model(obs[t], xy[t], rd[t])
+                logits, v = policy(obs[t], xy[t], rd[t])
             dist = torch.distributions.Categorical(logits=logits.float())
             a = dist.sample()
             act[t], logp[t], val[t] = a, dist.log_prob(a), v.float()
+            nvtx.range_pop()
             a1.record()
+            nvtx.range_push("rt_env_step")
             # the env writes observation maps, positions, rewards and done flags straight into the
             # rollout buffer's slots; the step's readings land in row `tick` of the readings sink
             env.step((a + 1).to(torch.int32), out_maps=obs[t + 1], out_xy=xy[t + 1], out_reward=rew[t],
                      out_done=dn[t])
             moments.standardize(readings[steps_in_episode], out=rd[t + 1])   # (count - mean) / max(std, 1)
+            nvtx.range_pop()
             a2.record()
             p_pairs.append((a0, a1))
             e_pairs.append((a1, a2))
             steps_in_episode += 1
             if steps_in_episode == 120:   # rollout of readings complete: fold into the running normaliser
-                moments.update(readings.view(-1))
-                merge_rollout_stats(moments, env.episode_stats())
+                nvtx.range_push("close_rollout")
+                local_m.update(readings.view(-1))
+                exchange.exchange(local_m, moments, env.episode_stats())   # all ranks: global <- chan(global, merged rollout)
                 x0, _ = env.reset(out_maps=obs[t + 1])
                 xy[t + 1].copy_(x0)
                 steps_in_episode = 0
+                nvtx.range_pop()
         u0, u1 = ev(), ev()
         u0.record()
+        nvtx.range_push("ppo_update")
         with torch.no_grad(), torch.autocast("cuda", dtype=amp, enabled=amp != torch.float32):
-            _, v_last = model(obs[T], xy[T], rd[T])
+            _, v_last = policy(obs[T], xy[T], rd[T])
         val[T] = v_last.float()
         adv = torch.zeros((T, E, A), dtype=torch.float32, device=dev)
         last = torch.zeros((E, A), device=dev)
@@ -144,6 +168,7 @@ def main():
             opt.zero_grad(set_to_none=True)
             loss.backward()
             opt.step()
+        nvtx.range_pop()
         u1.record()
         torch.cuda.synchronize()
         e = sum(p.elapsed_time(q) for p, q in e_pairs) / T
@@ -154,9 +179,12 @@ def main():
                     "env_fraction_of_iteration": e * T / (e * T + p * T + u), "loss": float(loss.detach())})
         obs[0].copy_(obs[T]); xy[0].copy_(xy[T]); rd[0].copy_(rd[T])
     if rank == 0:
-        print(json.dumps({"config": {"envs_per_gpu": E, "agents": A, "horizon": T, "gpus": world, "dtype": args.dtype},
+        print(json.dumps({"config": {"envs_per_gpu": E, "agents": A, "horizon": T, "gpus": world, "dtype": args.dtype,
+                                     "policy_chunk": chunk, "minibatches": args.minibatches,
+                                     "stats_exchange": exchange.backend},
                           "agent_steps_per_s_rollout": world * E * A / ((log[-1]["env_ms_per_step"] + log[-1]["policy_ms_per_step"]) * 1e-3),
                           "iters": log, "env_error_flags": env.errors()}))
+    exchange.close()
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -67,6 +67,10 @@ typedef struct rt_env rt_env;           /* batched environment (opaque)         
 typedef struct rt_welford rt_welford;   /* per-stream Welford standardisers      */
 typedef struct rt_moments rt_moments;   /* batch running moments (Chan-merged)   */
 typedef struct rt_estimator rt_estimator; /* per-cell median resampling estimator */
+typedef struct rt_comm rt_comm;         /* peer mailboxes of the ranks of one box */
+
+#define RT_COMM_MAX_RANKS 16    /* ranks (GPUs) of one box                       */
+#define RT_COMM_HANDLE_BYTES 64 /* exported mailbox handle (a CUDA IPC handle)   */
 
 /* One POD config across the ABI.  Stands in for the constructor kwargs of
  * SimpleGrid(start, terminal, size=10, render_mode=None)
@@ -278,7 +282,9 @@ int rt_moments_create(rt_moments** out);
 int rt_moments_destroy(rt_moments* m);
 int rt_moments_reset(rt_moments* m, void* stream);
 /* Fold n fp32 readings into the running (count, mean, M2): warp-shuffle /
- * block / grid Chan merges in a fixed order (deterministic for a given n). */
+ * block / grid Chan merges in a fixed order (deterministic for a given n and
+ * alignment).  x_dev: any contiguous float buffer (4-byte aligned; up to three
+ * readings in front of the first 16-byte boundary are folded singly). */
 int rt_moments_update(rt_moments* m, const float* x_dev, int64_t n, void* stream);
 /* out = (x - mean) / max(sqrt(M2/(count-1)), 1)  (standardize.py:74,93). */
 int rt_moments_standardize(rt_moments* m, const float* x_dev, float* out_dev, int64_t n,
@@ -291,6 +297,66 @@ int rt_moments_state(rt_moments* m, void** state_dev);
  * gathered_dev[r * stride_doubles] (device; stride >= 3). */
 int rt_moments_merge(rt_moments* m, const double* gathered_dev, int32_t n_ranks,
                      int32_t stride_doubles, void* stream);
+
+/* ---- multi-GPU: the once-per-rollout exchange -------
+ * The reference is single-process (simple_gridworld.py holds no cross-instance
+ * state, :58-65), so these entry points stand behind nothing in it: they are
+ * what lets envs shard over the GPUs of one box, one process per GPU.  `step`
+ * has no cross-GPU traffic; once per rollout every rank contributes six
+ * doubles — the moments of ITS readings of this rollout (count, mean, M2 of the
+ * rt_moments `local`) and its episode statistics (rt_env_episode_stats) — and
+ * every rank merges the rows in rank order: `global` <- chan(`global`,
+ * chan-merge over ranks of the locals), episode statistics summed, `local`
+ * cleared for the next rollout.  Same IEEE operations in the same order on every
+ * rank => bit-identical results.  `local` and `global` must be distinct handles
+ * (a running state that was also the per-rollout accumulator would be counted
+ * once per rank at the next merge).
+ *
+ * Two transports, same result:
+ *   (1) rt_stats_allgather_merge — ONE kernel per rank over peer-mapped
+ *       mailboxes (NVLink / NVSwitch): stores into every peer's mailbox, flag,
+ *       wait, merge.  No library collective, no host round trip, CUDA-graph
+ *       capturable.  Collective semantics: every rank must call it the same
+ *       number of times; a peer that does not arrive within the timeout
+ *       (RT_B200_COMM_TIMEOUT_MS, default 5000) sets a sticky error
+ *       (rt_comm_errors) instead of hanging the device.
+ *   (2) rt_stats_pack -> the caller's all-gather of 6 doubles per rank (NCCL
+ *       through torch.distributed, MPI, ...) -> rt_stats_merge_gathered. */
+
+/* Step 1 on every rank (current device = the rank's GPU): allocate this rank's
+ * mailbox and export its handle (RT_COMM_HANDLE_BYTES bytes, host).  world == 1
+ * needs no step 2. */
+int rt_comm_create(int32_t rank, int32_t world, rt_comm** out, void* handle_out_host);
+/* Step 2: the handles of ALL ranks in rank order (world x RT_COMM_HANDLE_BYTES,
+ * host), exchanged by the caller by any means; maps every peer's mailbox. */
+int rt_comm_connect(rt_comm* comm, const void* all_handles_host);
+/* Steps 1 + 2 for hosts without a communication library: the ranks of one box
+ * meet in the POSIX shared-memory object `name` ("/something", unique per job;
+ * removed again once every rank has connected).  Blocks until all ranks arrive. */
+int rt_comm_create_shm(const char* name, int32_t rank, int32_t world, rt_comm** out);
+/* Orderly shutdown: every rank calls rt_comm_disconnect (unmaps the peers'
+ * mailboxes; no further exchange), the caller synchronises the ranks by its own
+ * means, then every rank calls rt_comm_destroy (frees its own mailbox) — an
+ * exported mailbox must outlive its mappings in the other processes.
+ * rt_comm_destroy alone does both for this rank. */
+int rt_comm_disconnect(rt_comm* comm);
+int rt_comm_destroy(rt_comm* comm);
+/* Sticky error word -> *err_host (1 = a peer timed out).  Synchronises `stream`. */
+int rt_comm_errors(rt_comm* comm, int32_t* err_host, void* stream);
+
+/* Transport (1).  ep_stats_dev double [3] (may be NULL = zeros) is this rank's
+ * rt_env_episode_stats output; ep_merged_dev double [3] (may be NULL) receives
+ * the sums over ranks; gathered_out_dev double [world][6] (may be NULL) receives
+ * the gathered rows for inspection. */
+int rt_stats_allgather_merge(rt_comm* comm, rt_moments* local, rt_moments* global,
+                             const double* ep_stats_dev, double* ep_merged_dev,
+                             double* gathered_out_dev, void* stream);
+/* Transport (2): out6_dev double [6] = {count, mean, M2, episode stats}; then,
+ * after the caller's all-gather into gathered_dev double [n_ranks][6] (row r =
+ * rank r), the same merge as above. */
+int rt_stats_pack(rt_moments* local, const double* ep_stats_dev, double* out6_dev, void* stream);
+int rt_stats_merge_gathered(rt_moments* local, rt_moments* global, const double* gathered_dev,
+                            int32_t n_ranks, double* ep_merged_dev, void* stream);
 
 /* ---- Normalizer / BensLogNormalizer: src/math_utils/normalize.py ---------- */
 

@@ -16,6 +16,7 @@ from . import build as _build
 RT_OK, RT_ERR_BAD_ARG, RT_ERR_CUDA, RT_ERR_NOMEM, RT_ERR_BAD_ACTION, RT_ERR_ASSERT, RT_ERR_KEY = range(7)
 FLAG_BAD_ACTION, FLAG_LOG_FULL, FLAG_LAMBDA, FLAG_DRAWS, FLAG_NORMALIZE = 0x01, 0x02, 0x04, 0x08, 0x10
 MAX_AGENTS, MAX_POLYS, MAX_EDGES = 8, 5, 20
+COMM_MAX_RANKS, COMM_HANDLE_BYTES = 16, 64
 
 BUF = dict(
     AGENT_XY=0, PREV_DIST=1, START_XY=2, SRC_XY=3, SRC_INT=4, BKG=5, N_POLY=6, EDGES=7, TICK=8, EPISODE=9,
@@ -73,6 +74,15 @@ SYMBOLS = {
     "rt_moments_standardize": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "rt_moments_state": (C.c_int, [_vp, _pp]),
     "rt_moments_merge": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
+    "rt_comm_create": (C.c_int, [_i32, _i32, _pp, _vp]),
+    "rt_comm_connect": (C.c_int, [_vp, _vp]),
+    "rt_comm_create_shm": (C.c_int, [C.c_char_p, _i32, _i32, _pp]),
+    "rt_comm_disconnect": (C.c_int, [_vp]),
+    "rt_comm_destroy": (C.c_int, [_vp]),
+    "rt_comm_errors": (C.c_int, [_vp, C.POINTER(_i32), _vp]),
+    "rt_stats_allgather_merge": (C.c_int, [_vp] * 7),
+    "rt_stats_pack": (C.c_int, [_vp] * 4),
+    "rt_stats_merge_gathered": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "rt_normalize": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "rt_lognormalize": (C.c_int, [_vp, _dbl, _i32, _vp, _vp, _i64, _vp]),
     "rt_estimator_create": (C.c_int, [_i64, _i32, _i32, _pp]),

@@ -17,8 +17,8 @@ CSRC = PKG / "csrc"
 INCLUDE = PKG.parent / "include"
 LIB = PKG / "librt_b200.so"
 
-SOURCES = ["rt_host.cu", "rt_alloc.cu", "rt_env.cu", "rt_stats.cu"]
-HEADERS = ["rt_host.h", "rt_device.cuh", "rt_env_kernels.cuh"]
+SOURCES = ["rt_host.cu", "rt_alloc.cu", "rt_env.cu", "rt_stats.cu", "rt_comm.cu"]
+HEADERS = ["rt_host.h", "rt_device.cuh", "rt_env_kernels.cuh", "rt_moments.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -1,6 +1,7 @@
 // rt_env.cu — host side of the batched environment: handle, device slab, launches, C ABI.
 // See include/rt_b200.h for the contract of every entry point.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -12,6 +13,13 @@
 #include "rt_host.h"
 
 using namespace rt;
+
+#if defined(__x86_64__) || defined(__i386__)
+#include <immintrin.h>
+static inline void rt_cpu_relax() { _mm_pause(); }
+#else
+static inline void rt_cpu_relax() { std::atomic_signal_fence(std::memory_order_seq_cst); }
+#endif
 
 struct rt_env {
   rt_env_cfg cfg;
@@ -37,6 +45,9 @@ struct rt_env {
   bool lut_in_smem = true;
   cudaStream_t aux = nullptr;  // host path: results travel back here while the rasteriser streams
   cudaEvent_t ev_fork = nullptr;
+  unsigned long long host_seq = 0;   // host path: results of call k have landed when the pinned sequence word reads k
+  bool step_flags_dirty = true;      // the device word of voided-step flags may be non-zero (cleared lazily)
+  int d2h_ctas = 32;                 // CTAs of the result-return kernel (RT_B200_D2H_CTAS)
   int raster_ctas = 32, raster_unroll = 2;  // dense rasteriser: CTAs per SM (grid cap), chunks in flight per thread
   bool incremental = false;                 // rt_env_set_incremental: patch the caller's tensor when it is the same as last time
   const float* last_maps = nullptr;         // tensor that holds this env's latest observation
@@ -143,6 +154,47 @@ __global__ void k_or_flags(const int32_t* __restrict__ flags, int n, int32_t* __
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v |= flags[i];
   v = __reduce_or_sync(0xffffffffu, v);
   if ((threadIdx.x & 31) == 0 && v) atomicOr(out, v);
+}
+
+// Host path: ONE kernel returns a step's results — obs_xy, reward, done and the word of voided-step flags — to
+// (mapped) host memory, in place of four copy-engine requests.  16-byte stores where the destination allows;
+// the last CTA to finish publishes the flag word and then the call's sequence number, which the host polls.
+__device__ __forceinline__ void copy_to_host(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src,
+                                             size_t bytes, size_t tid, size_t nthreads) {
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const size_t n16 = bytes >> 4;
+    for (size_t i = tid; i < n16; i += nthreads)
+      reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+    for (size_t i = (n16 << 4) + tid; i < bytes; i += nthreads) dst[i] = src[i];
+  } else if ((reinterpret_cast<uintptr_t>(dst) & 3) == 0 && (bytes & 3) == 0) {
+    for (size_t i = tid; i < (bytes >> 2); i += nthreads)
+      reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(src)[i];
+  } else {
+    for (size_t i = tid; i < bytes; i += nthreads) dst[i] = src[i];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_results_to_host(const int32_t* __restrict__ xy, const int32_t* __restrict__ rw, const uint8_t* __restrict__ dn,
+                  size_t n, int32_t* __restrict__ h_xy, int32_t* __restrict__ h_rw, uint8_t* __restrict__ h_dn,
+                  int32_t* __restrict__ step_flags, unsigned* __restrict__ cta_counter, int32_t* __restrict__ h_flag,
+                  unsigned long long* __restrict__ h_seq, unsigned long long seq) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  copy_to_host(reinterpret_cast<unsigned char*>(h_xy), reinterpret_cast<const unsigned char*>(xy), n * 8, tid, nth);
+  copy_to_host(reinterpret_cast<unsigned char*>(h_rw), reinterpret_cast<const unsigned char*>(rw), n * 4, tid, nth);
+  copy_to_host(h_dn, dn, n, tid, nth);
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(cta_counter, 1u) == gridDim.x - 1) {  // every other CTA has fenced its stores
+      *cta_counter = 0u;
+      const int32_t f = *step_flags;
+      *step_flags = 0;
+      *reinterpret_cast<volatile int32_t*>(h_flag) = f;
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned long long*>(h_seq) = seq;
+    }
+  }
 }
 
 void launch_raster_vec(rt_env* h, float* obs_maps, cudaStream_t st) {
@@ -329,8 +381,9 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
   h->d_flag_or = (int32_t*)(base + o_for);
 
   // pinned staging: actions | obs_xy | reward | done | mask
-  h->pinned_bytes = E * A * 4 + E * A * 8 + E * A * 4 + E * A + E + 64;
+  h->pinned_bytes = ((E * A * 4 + E * A * 8 + E * A * 4 + E * A + E + 15) & ~(size_t)15) + 64;  // tail: flag word, sequence word
   RT_CUDA_OR(cudaHostAlloc((void**)&h->pinned, h->pinned_bytes, cudaHostAllocDefault), { rt_env_destroy(h); });
+  std::memset(h->pinned + h->pinned_bytes - 64, 0, 64);
 
   EnvDev& d = h->dev;
   d.E = cfg->n_envs; d.A = cfg->n_agents; d.G = cfg->grid; d.cells = (int)cells;
@@ -418,6 +471,7 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
     if (v >= 1 && v * cfg->n_agents <= 192) h->epb = v;
   }
   if (const char* ev = std::getenv("RT_B200_ZEROCOPY")) h->zerocopy = std::atoi(ev) != 0;
+  if (const char* ev = std::getenv("RT_B200_D2H_CTAS")) h->d2h_ctas = std::min(1024, std::max(1, std::atoi(ev)));
   if (const char* ev = std::getenv("RT_B200_RASTER_CTAS")) h->raster_ctas = std::max(1, std::atoi(ev));
   if (const char* ev = std::getenv("RT_B200_RASTER_UNROLL")) h->raster_unroll = std::max(1, std::atoi(ev));
   if (const char* ev = std::getenv("RT_B200_SPARSE_CTAS")) h->sparse_ctas = std::max(1, std::atoi(ev));
@@ -501,6 +555,7 @@ int rt_env_step(rt_env* h, const int32_t* actions_dev, int32_t* obs_xy_dev, floa
                 int32_t* reward_dev, uint8_t* done_dev, void* stream) {
   if (!h || !actions_dev || !obs_xy_dev || !reward_dev || !done_dev) return RT_ERR_BAD_ARG;
   RtDeviceGuard on_device(h->device);
+  h->step_flags_dirty = true;
   return launch_step(h, actions_dev, obs_xy_dev, obs_maps_dev, reward_dev, done_dev,
                      (cudaStream_t)stream);
 }
@@ -546,6 +601,8 @@ int rt_env_step_host(rt_env* h, const int32_t* actions_host, int32_t* obs_xy_hos
   unsigned char* p_xy = h->pinned + n * 4;
   unsigned char* p_rw = h->pinned + n * 12;
   unsigned char* p_dn = h->pinned + n * 16;
+  int32_t* p_fl = reinterpret_cast<int32_t*>(h->pinned + h->pinned_bytes - 16);
+  volatile unsigned long long* p_seq = reinterpret_cast<volatile unsigned long long*>(h->pinned + h->pinned_bytes - 8);
   // Invalid actions are caught on the device: the env's step is voided (the reference raises before any
   // state change, simple_gridworld.py:138) and a flag word travels back with the results.
   // Pinned (mapped) caller memory is read by k_step directly over PCIe — no separate H2D copy in front
@@ -562,27 +619,47 @@ int rt_env_step_host(rt_env* h, const int32_t* actions_host, int32_t* obs_xy_hos
     }
     RT_CUDA(cudaMemcpyAsync(h->d_actions, a_src, n * 4, cudaMemcpyDefault, st));
   }
-  RT_CUDA(cudaMemsetAsync(h->dev.step_flags, 0, 4, st));
-  // k_step, then the small results travel back on the auxiliary stream WHILE the rasteriser streams
+  if (h->step_flags_dirty) {  // only after device-path steps: the return kernel below leaves the word cleared
+    RT_CUDA(cudaMemsetAsync(h->dev.step_flags, 0, 4, st));
+    h->step_flags_dirty = false;
+  }
+  // k_step, then ONE kernel on the auxiliary stream writes the small results straight into (mapped) host memory
+  // WHILE the rasteriser streams on `st`: caller buffers when they are pinned, the handle's staging otherwise.
   int rc = launch_step(h, actions_dev, h->d_obs_xy, nullptr, h->d_reward, h->d_done, st, obs_maps_dev != nullptr);
+  h->step_flags_dirty = false;
   if (rc != RT_OK) return rc;
   RT_CUDA(cudaEventRecord(h->ev_fork, st));
   RT_CUDA(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
-  const bool dx = is_pinned_or_device(obs_xy_host), dr = is_pinned_or_device(reward_host),
-             dd = is_pinned_or_device(done_host);
-  RT_CUDA(cudaMemcpyAsync(dx ? (void*)obs_xy_host : (void*)p_xy, h->d_obs_xy, n * 8, cudaMemcpyDefault, h->aux));
-  RT_CUDA(cudaMemcpyAsync(dr ? (void*)reward_host : (void*)p_rw, h->d_reward, n * 4, cudaMemcpyDefault, h->aux));
-  RT_CUDA(cudaMemcpyAsync(dd ? (void*)done_host : (void*)p_dn, h->d_done, n, cudaMemcpyDefault, h->aux));
-  int32_t* p_fl = reinterpret_cast<int32_t*>(h->pinned + h->pinned_bytes - 16);
-  RT_CUDA(cudaMemcpyAsync(p_fl, h->dev.step_flags, 4, cudaMemcpyDeviceToHost, h->aux));
+  void* ax = const_cast<void*>(device_alias(obs_xy_host));
+  void* ar = const_cast<void*>(device_alias(reward_host));
+  void* ad = const_cast<void*>(device_alias(done_host));
+  const bool dx = ax != nullptr, dr = ar != nullptr, dd = ad != nullptr;
+  const unsigned long long seq = ++h->host_seq;
+  k_results_to_host<<<(unsigned)h->d2h_ctas, 256, 0, h->aux>>>(
+      h->d_obs_xy, h->d_reward, h->d_done, n, static_cast<int32_t*>(dx ? ax : (void*)p_xy),
+      static_cast<int32_t*>(dr ? ar : (void*)p_rw), static_cast<uint8_t*>(dd ? ad : (void*)p_dn), h->dev.step_flags,
+      reinterpret_cast<unsigned*>(h->d_flag_or + 2), p_fl, const_cast<unsigned long long*>(p_seq), seq);
+  h->launches += 1;
+  RT_CUDA_LAUNCH_CHECK();
   if (obs_maps_dev) {
     rc = raster_or_patch(h, obs_maps_dev, st);
     if (rc != RT_OK) return rc;
   }
-  // Return when the step's results are in host memory.  The rasteriser keeps streaming on `st`: whatever
-  // the host does before its next call (the policy's bookkeeping, the next call's own launch latency) hides
-  // under it, and everything enqueued on `st` later is ordered behind it.
-  RT_CUDA(cudaStreamSynchronize(h->aux));
+  // Return when the step's results are in host memory: poll the sequence word the return kernel publishes last
+  // (no driver call on the wait).  The rasteriser keeps streaming on `st`: whatever the host does before its next
+  // call hides under it, and everything enqueued on `st` later is ordered behind it.
+  for (unsigned spins = 0; *p_seq != seq;) {
+    rt_cpu_relax();
+    if ((++spins & 0xfffffu) == 0 && cudaStreamQuery(h->aux) != cudaErrorNotReady) {  // finished or failed
+      if (*p_seq == seq) break;
+      RT_CUDA(cudaStreamSynchronize(h->aux));
+      if (*p_seq != seq) {
+        rt_note_error_text("rt_env_step_host: result-return kernel finished without publishing its results");
+        return RT_ERR_CUDA;
+      }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
   if (!dx) std::memcpy(obs_xy_host, p_xy, n * 8);
   if (!dr) std::memcpy(reward_host, p_rw, n * 4);
   if (!dd) std::memcpy(done_host, p_dn, n);
@@ -636,6 +713,8 @@ int rt_env_buffer(rt_env* h, int which, void** dev_ptr, size_t* bytes) {
   if ((which == RT_BUF_INTENSITY || which == RT_BUF_VISIT) && !h->dev.live_dense) {
     // sparse mode keeps visits / intensities in the records only: bring the dense views up to date (synchronises)
     RT_CUDA(cudaDeviceSynchronize());
+    RT_CUDA(cudaMemset(h->dev.visit, 0, h->buf_bytes[RT_BUF_VISIT]));  // resets leave the dense views alone in sparse mode
+    RT_CUDA(cudaMemset(h->dev.inten, 0, h->buf_bytes[RT_BUF_INTENSITY]));
     k_densify<<<(unsigned)((h->dev.E + 127) / 128), 128>>>(h->dev);
     h->launches += 1;
     RT_CUDA_LAUNCH_CHECK();

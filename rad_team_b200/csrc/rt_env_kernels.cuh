@@ -677,6 +677,9 @@ k_zero_maps(const EnvDev d, const uint8_t* __restrict__ mask) {
   } else {
     for (size_t i = threadIdx.x * 8; i < b64; i += blockDim.x * 8) *reinterpret_cast<uint2*>(c + i) = make_uint2(0u, 0u);
   }
+  // the dense visit / intensity maps are only kept when a dense rasteriser reads them; otherwise they are
+  // materialised on request (rt_env_buffer clears them first) and a reset has 8 of 14 KB per env to clear
+  if (!d.live_dense) return;
   if ((d.cells & 7) == 0) {
     for (size_t i = threadIdx.x * 16; i < b16; i += blockDim.x * 16) *reinterpret_cast<uint4*>(v + i) = z;
     for (size_t i = threadIdx.x * 16; i < b32; i += blockDim.x * 16) *reinterpret_cast<uint4*>(f + i) = z;

@@ -24,6 +24,14 @@ struct RtDeviceGuard {
   RtDeviceGuard& operator=(const RtDeviceGuard&) = delete;
 };
 
+// K4b handle (rt_stats.cu); rt_comm.cu merges into / out of its state.
+struct rt_moments {
+  int device = 0;
+  double* state = nullptr;     // [3] count, mean, M2
+  double* partials = nullptr;  // [max_blocks][3]
+  int max_blocks = 0;
+};
+
 #define RT_CUDA(call)                         \
   do {                                        \
     cudaError_t rt_e_ = (call);               \

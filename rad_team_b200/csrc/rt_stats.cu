@@ -11,6 +11,7 @@
 
 #include "rt_device.cuh"
 #include "rt_host.h"
+#include "rt_moments.cuh"
 
 using namespace rt;
 
@@ -169,30 +170,9 @@ int rt_welford_buffers(rt_welford* w, void** state_dev, void** count_dev) {
 // partial triple.  Pass 2 (k_moments_final, one warp) merges the CTA partials in index order and
 // folds the result into the running state.  Every merge order is fixed by (n, grid), so the result
 // is deterministic run to run; it differs from the sequential recurrence only by rounding.
-struct rt_moments {
-  int device = 0;
-  double* state = nullptr;     // [3]
-  double* partials = nullptr;  // [max_blocks][3]
-  int max_blocks = 0;
-};
+// (struct rt_moments lives in rt_host.h: rt_comm.cu launches on its state too)
 
 namespace {
-
-struct Mom {
-  double n, mean, m2;
-};
-
-__device__ __forceinline__ Mom chan(const Mom a, const Mom b) {
-  if (b.n == 0.0) return a;
-  if (a.n == 0.0) return b;
-  Mom r;
-  r.n = a.n + b.n;
-  const double delta = b.mean - a.mean;
-  const double f = b.n / r.n;
-  r.mean = a.mean + delta * f;
-  r.m2 = a.m2 + b.m2 + delta * delta * (a.n * f);
-  return r;
-}
 
 __device__ __forceinline__ Mom warp_merge(Mom m) {
 #pragma unroll
@@ -238,8 +218,12 @@ constexpr int kMomThreads = 256;
 constexpr int kMomUnroll = 4;  // 16-byte loads in flight per thread
 
 __global__ void __launch_bounds__(kMomThreads)
-k_moments_partial(const float* __restrict__ x, long long n, double* __restrict__ partials) {
+k_moments_partial(const float* __restrict__ x0, long long n0, int head, double* __restrict__ partials) {
+  // x0 may start anywhere on a 4-byte boundary (a row of a [T, E, A] buffer, a slice): its first `head` (< 4)
+  // readings are folded one by one like the tail, the 16-byte vector body starts at the aligned x
   __shared__ Mom s_w[kMomThreads / 32];
+  const float* __restrict__ x = x0 + head;
+  const long long n = n0 - head;
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * kMomThreads;
   long long i = (long long)blockIdx.x * kMomThreads + threadIdx.x;
@@ -263,6 +247,10 @@ k_moments_partial(const float* __restrict__ x, long long n, double* __restrict__
   // tail (n % 4 readings): one single-reading merge each, by the first threads of block 0
   if (blockIdx.x == 0 && threadIdx.x < (int)(n & 3)) {
     Mom q = {1.0, (double)x[(n4 << 2) + threadIdx.x], 0.0};
+    acc = chan(acc, q);
+  }
+  if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 32 + head) {  // head: threads of the second warp
+    Mom q = {1.0, (double)x0[threadIdx.x - 32], 0.0};
     acc = chan(acc, q);
   }
   acc = warp_merge(acc);
@@ -323,8 +311,12 @@ __global__ void k_moments_merge(const double* __restrict__ gathered, int n_ranks
 }
 
 __global__ void __launch_bounds__(256)
-k_moments_standardize(const double* __restrict__ state, const float* __restrict__ x, float* __restrict__ out,
-                      long long n) {
+k_moments_standardize(const double* __restrict__ state, const float* __restrict__ x0, float* __restrict__ out0,
+                      long long n0, int head) {
+  // head (< 4): readings in front of the first 16-byte boundary, when input and output share their misalignment
+  const float* __restrict__ x = x0 + head;
+  float* __restrict__ out = out0 + head;
+  const long long n = n0 - head;
   const double cnt = state[0], mean = state[1], m2 = state[2];
   double sd = 1.0;
   if (cnt >= 2.0) {
@@ -360,6 +352,23 @@ k_moments_standardize(const double* __restrict__ state, const float* __restrict_
     const long long j = (n4 << 2) + threadIdx.x;
     out[j] = (float)(((double)x[j] - mean) * inv);
   }
+  if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 32 + head)
+    out0[threadIdx.x - 32] = (float)(((double)x0[threadIdx.x - 32] - mean) * inv);
+}
+
+// input and output misaligned DIFFERENTLY with respect to 16 bytes: 4-byte accesses (rare; same arithmetic)
+__global__ void __launch_bounds__(256)
+k_moments_standardize_scalar(const double* __restrict__ state, const float* __restrict__ x, float* __restrict__ out,
+                             long long n) {
+  const double cnt = state[0], mean = state[1], m2 = state[2];
+  double sd = 1.0;
+  if (cnt >= 2.0) {
+    const double s = sqrt(m2 / (cnt - 1.0));
+    sd = s > 1.0 ? s : 1.0;
+  }
+  const double inv = 1.0 / sd;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = (float)(((double)x[i] - mean) * inv);
 }
 
 }  // namespace
@@ -409,12 +418,16 @@ int rt_moments_reset(rt_moments* m, void* stream) {
 int rt_moments_update(rt_moments* m, const float* x_dev, int64_t n, void* stream) {
   if (!m || !x_dev || n < 0) return RT_ERR_BAD_ARG;
   RtDeviceGuard on_device(m->device);
-  if (((uintptr_t)x_dev & 15) != 0) return RT_ERR_BAD_ARG;  // 16-byte vector loads
+  if (((uintptr_t)x_dev & 3) != 0) return RT_ERR_BAD_ARG;  // not even a float boundary
   if (n == 0) return RT_OK;
-  long long blocks = ((n >> 2) + kMomThreads * kMomUnroll - 1) / (kMomThreads * kMomUnroll);
+  // any contiguous float32 view works (a row readings[t] of a [T, E, A] buffer, x[1:]): up to three readings in
+  // front of the first 16-byte boundary are folded singly, the vector loads start at the boundary
+  int head = (int)(((16 - ((uintptr_t)x_dev & 15)) & 15) >> 2);
+  if (head > n) head = (int)n;
+  long long blocks = (((n - head) >> 2) + kMomThreads * kMomUnroll - 1) / (kMomThreads * kMomUnroll);
   if (blocks < 1) blocks = 1;
   if (blocks > m->max_blocks) blocks = m->max_blocks;
-  k_moments_partial<<<(unsigned)blocks, kMomThreads, 0, (cudaStream_t)stream>>>(x_dev, n, m->partials);
+  k_moments_partial<<<(unsigned)blocks, kMomThreads, 0, (cudaStream_t)stream>>>(x_dev, n, head, m->partials);
   k_moments_final<<<1, kFinalThreads, 0, (cudaStream_t)stream>>>(m->partials, (int)blocks, m->state, 0);
   RT_CUDA_LAUNCH_CHECK();
   return RT_OK;
@@ -423,12 +436,18 @@ int rt_moments_update(rt_moments* m, const float* x_dev, int64_t n, void* stream
 int rt_moments_standardize(rt_moments* m, const float* x_dev, float* out_dev, int64_t n, void* stream) {
   if (!m || !x_dev || !out_dev || n < 0) return RT_ERR_BAD_ARG;
   RtDeviceGuard on_device(m->device);
-  if ((((uintptr_t)x_dev | (uintptr_t)out_dev) & 15) != 0) return RT_ERR_BAD_ARG;
+  if ((((uintptr_t)x_dev | (uintptr_t)out_dev) & 3) != 0) return RT_ERR_BAD_ARG;
   if (n == 0) return RT_OK;
   long long blocks = ((n >> 2) + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > (long long)m->max_blocks * 4) blocks = (long long)m->max_blocks * 4;
-  k_moments_standardize<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(m->state, x_dev, out_dev, n);
+  if ((((uintptr_t)x_dev ^ (uintptr_t)out_dev) & 15) != 0) {  // no common 16-byte phase: 4-byte accesses
+    k_moments_standardize_scalar<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(m->state, x_dev, out_dev, n);
+  } else {
+    int head = (int)(((16 - ((uintptr_t)x_dev & 15)) & 15) >> 2);
+    if (head > n) head = (int)n;
+    k_moments_standardize<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(m->state, x_dev, out_dev, n, head);
+  }
   RT_CUDA_LAUNCH_CHECK();
   return RT_OK;
 }
@@ -556,8 +575,9 @@ k_est_update(const rt_estimator s, const int32_t* __restrict__ key, const double
   if (i >= s.n) return;
   const int k = key[i];
   const int idx = s.used[i];
-  if (k < 0 || k >= s.n_keys || idx >= s.capacity) {
-    if (err) err[i] = RT_ERR_BAD_ARG;
+  if (k < 0 || k >= s.n_keys || idx >= s.capacity) {  // key out of range / reading pool full
+    if (err) err[i] = idx >= s.capacity ? RT_ERR_NOMEM : RT_ERR_BAD_ARG;
+    if (est_out) est_out[i] = CUDART_NAN;  // never leave the output uninitialised
     return;
   }
   const double v = value[i];

@@ -54,7 +54,12 @@ class RadSearchVectorEnv(_Base):
 
     def step(self, actions) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray, Dict[str, Any]]:
         act = np.ascontiguousarray(actions, dtype=np.int32).reshape(self.num_envs, self.n_agents)
-        xy, rew, done, _, _ = self.env.step(act)          # ValueError("... is not a valid Action") as the reference
+        # The reference raises before touching any state (simple_gridworld.py:138).  Checked here, on the host, so a
+        # bad action advances NO env (the device would void only the offending envs and step the others).
+        bad = (act < 1) | (act > 4)
+        if bad.any():
+            raise ValueError(f"{int(act[bad][0])} is not a valid Action")
+        xy, rew, done, _, _ = self.env.step(act)
         self._tick += 1
         terminated = done.astype(bool).any(axis=1)
         truncated = (self._tick >= self.max_steps) & ~terminated
@@ -69,6 +74,10 @@ class RadSearchVectorEnv(_Base):
             self._tick[finished] = 0
         infos.update(self._infos())
         return obs, rewards, terminated, truncated, infos
+
+    def errors(self) -> int:
+        """OR of the envs' sticky RT_FLAG_* bits (include/rt_b200.h); 0 in a healthy run.  Synchronises."""
+        return self.env.errors()
 
     def close(self, **kwargs: Any) -> None:
         if not self.closed:

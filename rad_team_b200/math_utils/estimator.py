@@ -88,6 +88,7 @@ class IntensityResamplingEstimator:
     def __init__(self, n_keys: int = 4096, capacity: int = 4096) -> None:
         self._b = BatchedEstimator(1, n_keys, capacity)
         self._slot: Dict[Tuple[int, int], int] = {}
+        self._n_readings = 0
 
     # reference attributes
     @property
@@ -105,12 +106,18 @@ class IntensityResamplingEstimator:
     def reset(self) -> None:
         self._b.reset()
         self._slot = {}
+        self._n_readings = 0
 
     def update(self, key: Tuple[int, int], value: float) -> None:
         if key not in self._slot:
             if len(self._slot) >= self._b.n_keys:
-                raise MemoryError("estimator key slots exhausted")
+                raise MemoryError(f"estimator key slots exhausted (n_keys={self._b.n_keys}; the reference's dict is "
+                                  "unbounded — construct with a larger n_keys)")
             self._slot[key] = len(self._slot)
+        if self._n_readings >= self._b.capacity:  # the device log is a fixed pool, the reference's lists are unbounded
+            raise MemoryError(f"estimator reading capacity exhausted (capacity={self._b.capacity} readings in total "
+                              "over all keys — construct with a larger capacity)")
+        self._n_readings += 1
         _, err = self._b.update([self._slot[key]], [float(value)])
         _lib.check(int(err[0].item()), "estimator update")
 
