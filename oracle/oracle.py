@@ -282,6 +282,18 @@ def moments_standardize(state, x):
     return out
 
 
+def rect_blocks(segs, rect):
+    """uint8[n]: does segment i = (px, py, qx, qy) hit at least one edge of the rectangle (x0, y0, x1, y1)?"""
+    s = np.ascontiguousarray(segs, np.float32).reshape(-1, 4)
+    r = np.ascontiguousarray(rect, np.float32)
+    out = np.zeros(s.shape[0], np.uint8)
+    f = lib().orc_rect_blocks_batch
+    f.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    f.restype = None
+    f(_p(s), s.shape[0], _p(r), _p(out))
+    return out
+
+
 def segment_hits(seg, edge):
     s = np.ascontiguousarray(seg, np.float32)
     e = np.ascontiguousarray(edge, np.float32)

@@ -497,6 +497,18 @@ static int polys_crossed(const orc_one* s, float px, float py, float qx, float q
 int orc_segment_hits(const float seg[4], const float edge[4]) {
   return seg_hits_edge(seg[0], seg[1], seg[2], seg[3], edge);
 }
+/* Batch form for the exhaustive predicate tests: out[i] = 1 when segment i = (px,py,qx,qy) hits at least one of
+ * the four edges of the axis-aligned rectangle (x0,y0,x1,y1), the edges built in the order scenario generation
+ * uses — i.e. whether that obstruction counts towards n_blocked. */
+void orc_rect_blocks_batch(const float* seg, int64_t n, const float rect[4], uint8_t* out) {
+  const float X0 = rect[0], Y0 = rect[1], X1 = rect[2], Y1 = rect[3];
+  const float e[4][4] = {{X0, Y0, X1, Y0}, {X1, Y0, X1, Y1}, {X1, Y1, X0, Y1}, {X0, Y1, X0, Y0}};
+  for (int64_t i = 0; i < n; ++i) {
+    int hit = 0;
+    for (int j = 0; j < 4; ++j) hit |= seg_hits_edge(seg[4 * i], seg[4 * i + 1], seg[4 * i + 2], seg[4 * i + 3], e[j]);
+    out[i] = (uint8_t)hit;
+  }
+}
 
 static int l1(const int32_t a[2], const int32_t b[2]) { return abs(a[0] - b[0]) + abs(a[1] - b[1]); }
 

@@ -46,8 +46,6 @@ struct rt_env {
   cudaStream_t aux = nullptr;  // host path: results travel back here while the rasteriser streams
   cudaEvent_t ev_fork = nullptr;
   unsigned long long host_seq = 0;   // host path: results of call k have landed when the pinned sequence word reads k
-  bool step_flags_dirty = true;      // the device word of voided-step flags may be non-zero (cleared lazily)
-  int d2h_ctas = 32;                 // CTAs of the result-return kernel (RT_B200_D2H_CTAS)
   int raster_ctas = 32, raster_unroll = 2;  // dense rasteriser: CTAs per SM (grid cap), chunks in flight per thread
   bool incremental = false;                 // rt_env_set_incremental: patch the caller's tensor when it is the same as last time
   const float* last_maps = nullptr;         // tensor that holds this env's latest observation
@@ -156,47 +154,6 @@ __global__ void k_or_flags(const int32_t* __restrict__ flags, int n, int32_t* __
   if ((threadIdx.x & 31) == 0 && v) atomicOr(out, v);
 }
 
-// Host path: ONE kernel returns a step's results — obs_xy, reward, done and the word of voided-step flags — to
-// (mapped) host memory, in place of four copy-engine requests.  16-byte stores where the destination allows;
-// the last CTA to finish publishes the flag word and then the call's sequence number, which the host polls.
-__device__ __forceinline__ void copy_to_host(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src,
-                                             size_t bytes, size_t tid, size_t nthreads) {
-  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-    const size_t n16 = bytes >> 4;
-    for (size_t i = tid; i < n16; i += nthreads)
-      reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
-    for (size_t i = (n16 << 4) + tid; i < bytes; i += nthreads) dst[i] = src[i];
-  } else if ((reinterpret_cast<uintptr_t>(dst) & 3) == 0 && (bytes & 3) == 0) {
-    for (size_t i = tid; i < (bytes >> 2); i += nthreads)
-      reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(src)[i];
-  } else {
-    for (size_t i = tid; i < bytes; i += nthreads) dst[i] = src[i];
-  }
-}
-
-__global__ void __launch_bounds__(256)
-k_results_to_host(const int32_t* __restrict__ xy, const int32_t* __restrict__ rw, const uint8_t* __restrict__ dn,
-                  size_t n, int32_t* __restrict__ h_xy, int32_t* __restrict__ h_rw, uint8_t* __restrict__ h_dn,
-                  int32_t* __restrict__ step_flags, unsigned* __restrict__ cta_counter, int32_t* __restrict__ h_flag,
-                  unsigned long long* __restrict__ h_seq, unsigned long long seq) {
-  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
-  copy_to_host(reinterpret_cast<unsigned char*>(h_xy), reinterpret_cast<const unsigned char*>(xy), n * 8, tid, nth);
-  copy_to_host(reinterpret_cast<unsigned char*>(h_rw), reinterpret_cast<const unsigned char*>(rw), n * 4, tid, nth);
-  copy_to_host(h_dn, dn, n, tid, nth);
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (atomicAdd(cta_counter, 1u) == gridDim.x - 1) {  // every other CTA has fenced its stores
-      *cta_counter = 0u;
-      const int32_t f = *step_flags;
-      *step_flags = 0;
-      *reinterpret_cast<volatile int32_t*>(h_flag) = f;
-      __threadfence_system();
-      *reinterpret_cast<volatile unsigned long long*>(h_seq) = seq;
-    }
-  }
-}
-
 void launch_raster_vec(rt_env* h, float* obs_maps, cudaStream_t st) {
   const EnvDev& d = h->dev;
   const long long n_chunks = (long long)d.E * (d.cells >> 3);
@@ -268,7 +225,8 @@ int raster_or_patch(rt_env* h, float* obs_maps, cudaStream_t st) {
 
 int launch_step(rt_env* h, const int32_t* actions, int32_t* obs_xy, float* obs_maps, int32_t* reward,
                 uint8_t* done, cudaStream_t st, bool raster_follows = false) {
-  const EnvDev& d = h->dev;
+  EnvDev d = h->dev;
+  d.host_seq = h->host_seq;
   const int epb = h->epb;
   const unsigned blocks = (unsigned)((d.E + epb - 1) / epb);
   RT_CUDA(launch_pdl(k_step, blocks, (unsigned)(epb * d.A), step_smem_bytes(epb, d.A), st, h->pdl, d, actions, obs_xy,
@@ -352,8 +310,10 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
   Carver cv;
   size_t off[RT_BUF__COUNT];
   for (int i = 0; i < RT_BUF__COUNT; ++i) off[i] = cv.take(sz[i]);
-  const size_t o_act = cv.take(E * A * 4), o_xy = cv.take(E * A * 8), o_rw = cv.take(E * A * 4),
-               o_dn = cv.take(E * A), o_mask = cv.take(E), o_for = cv.take(16), o_prev = cv.take(E * 16);
+  // host path: obs_xy | reward | done packed back to back, so that ONE copy returns them when the caller's
+  // buffers are laid out the same way
+  const size_t o_act = cv.take(E * A * 4), o_xy = cv.take(E * A * 13), o_rw = o_xy + E * A * 8,
+               o_dn = o_xy + E * A * 12, o_mask = cv.take(E), o_for = cv.take(32), o_prev = cv.take(E * 16);
   h->slab_bytes = cv.off;
   if (const char* ev = std::getenv("RT_B200_SLAB_COMPRESS")) h->slab_vmm = std::atoi(ev) != 0;
   if (h->slab_vmm) {
@@ -427,7 +387,8 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
   d.rec_stride = rec_stride;
   d.rec_prefix = rec_stride < 128 ? rec_stride : 128;  // 1 KB per env covers 125 visited cells; the rest is read directly
   d.rollout = nullptr;
-  d.step_flags = h->d_flag_or + 1;
+  d.step_flags = h->d_flag_or + 4;  // {flags of odd calls, of even calls, sequence number (8 B)}, 16-byte aligned
+  d.host_seq = 0;
   d.prev_cells = (uint4*)(base + o_prev);
   d.inj = nullptr;
   d.inj_k = 0;
@@ -471,7 +432,7 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
     if (v >= 1 && v * cfg->n_agents <= 192) h->epb = v;
   }
   if (const char* ev = std::getenv("RT_B200_ZEROCOPY")) h->zerocopy = std::atoi(ev) != 0;
-  if (const char* ev = std::getenv("RT_B200_D2H_CTAS")) h->d2h_ctas = std::min(1024, std::max(1, std::atoi(ev)));
+
   if (const char* ev = std::getenv("RT_B200_RASTER_CTAS")) h->raster_ctas = std::max(1, std::atoi(ev));
   if (const char* ev = std::getenv("RT_B200_RASTER_UNROLL")) h->raster_unroll = std::max(1, std::atoi(ev));
   if (const char* ev = std::getenv("RT_B200_SPARSE_CTAS")) h->sparse_ctas = std::max(1, std::atoi(ev));
@@ -555,7 +516,6 @@ int rt_env_step(rt_env* h, const int32_t* actions_dev, int32_t* obs_xy_dev, floa
                 int32_t* reward_dev, uint8_t* done_dev, void* stream) {
   if (!h || !actions_dev || !obs_xy_dev || !reward_dev || !done_dev) return RT_ERR_BAD_ARG;
   RtDeviceGuard on_device(h->device);
-  h->step_flags_dirty = true;
   return launch_step(h, actions_dev, obs_xy_dev, obs_maps_dev, reward_dev, done_dev,
                      (cudaStream_t)stream);
 }
@@ -577,17 +537,34 @@ int rt_env_reset_host(rt_env* h, const uint8_t* mask_host, int32_t* obs_xy_host,
     RT_CUDA(cudaMemcpyAsync(h->d_mask, srcp, E, cudaMemcpyDefault, st));
     mask_dev = h->d_mask;
   }
-  const int rc = launch_reset(h, mask_dev, h->d_obs_xy, obs_maps_dev, st);
-  if (rc != RT_OK) return rc;
+  // k_reset_state writes the start positions; they travel back on the auxiliary stream while the map clears and the
+  // rasteriser run on `st`, and the call returns when they have landed (as rt_env_step_host does)
+  const EnvDev& d = h->dev;
+  k_reset_state<<<(unsigned)((d.E + 127) / 128), 128, 0, st>>>(d, mask_dev, h->d_obs_xy);
+  h->launches += 1;
+  RT_CUDA_LAUNCH_CHECK();
+  bool direct = false;
   if (obs_xy_host) {
-    const bool direct = is_pinned_or_device(obs_xy_host);
+    RT_CUDA(cudaEventRecord(h->ev_fork, st));
+    RT_CUDA(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
+    direct = is_pinned_or_device(obs_xy_host);
     void* dst = direct ? (void*)obs_xy_host : (void*)(h->pinned + E * A * 4);
-    RT_CUDA(cudaMemcpyAsync(dst, h->d_obs_xy, E * A * 8, cudaMemcpyDefault, st));
-    RT_CUDA(cudaStreamSynchronize(st));
-    if (!direct) std::memcpy(obs_xy_host, dst, E * A * 8);
-  } else {
-    RT_CUDA(cudaStreamSynchronize(st));
+    RT_CUDA(cudaMemcpyAsync(dst, h->d_obs_xy, E * A * 8, cudaMemcpyDefault, h->aux));
   }
+  k_zero_maps<<<(unsigned)d.E, 256, 0, st>>>(d, mask_dev);
+  h->launches += 1;
+  RT_CUDA_LAUNCH_CHECK();
+  if (obs_maps_dev) {
+    const int rc = launch_raster(h, obs_maps_dev, st);
+    if (rc != RT_OK) return rc;
+  } else {
+    h->last_maps = nullptr;
+  }
+  if (obs_xy_host) {
+    RT_CUDA(cudaStreamSynchronize(h->aux));
+    if (!direct) std::memcpy(obs_xy_host, h->pinned + E * A * 4, E * A * 8);
+  }
+  if (mask_host) RT_CUDA(cudaStreamSynchronize(st));  // the staged mask must stay put until the kernels have read it
   return RT_OK;
 }
 
@@ -601,7 +578,8 @@ int rt_env_step_host(rt_env* h, const int32_t* actions_host, int32_t* obs_xy_hos
   unsigned char* p_xy = h->pinned + n * 4;
   unsigned char* p_rw = h->pinned + n * 12;
   unsigned char* p_dn = h->pinned + n * 16;
-  int32_t* p_fl = reinterpret_cast<int32_t*>(h->pinned + h->pinned_bytes - 16);
+  // tail of the pinned block: {flags of odd calls, flags of even calls, sequence number} as the device keeps them
+  volatile int32_t* p_fl = reinterpret_cast<volatile int32_t*>(h->pinned + h->pinned_bytes - 16);
   volatile unsigned long long* p_seq = reinterpret_cast<volatile unsigned long long*>(h->pinned + h->pinned_bytes - 8);
   // Invalid actions are caught on the device: the env's step is voided (the reference raises before any
   // state change, simple_gridworld.py:138) and a flag word travels back with the results.
@@ -619,42 +597,42 @@ int rt_env_step_host(rt_env* h, const int32_t* actions_host, int32_t* obs_xy_hos
     }
     RT_CUDA(cudaMemcpyAsync(h->d_actions, a_src, n * 4, cudaMemcpyDefault, st));
   }
-  if (h->step_flags_dirty) {  // only after device-path steps: the return kernel below leaves the word cleared
-    RT_CUDA(cudaMemsetAsync(h->dev.step_flags, 0, 4, st));
-    h->step_flags_dirty = false;
-  }
-  // k_step, then ONE kernel on the auxiliary stream writes the small results straight into (mapped) host memory
-  // WHILE the rasteriser streams on `st`: caller buffers when they are pinned, the handle's staging otherwise.
+  // k_step (it stamps this call's sequence number next to the flag word and clears the word of the NEXT call: no
+  // memset), then the small results travel back on the auxiliary stream WHILE the rasteriser streams on `st`.
+  const unsigned long long seq = ++h->host_seq;
   int rc = launch_step(h, actions_dev, h->d_obs_xy, nullptr, h->d_reward, h->d_done, st, obs_maps_dev != nullptr);
-  h->step_flags_dirty = false;
   if (rc != RT_OK) return rc;
   RT_CUDA(cudaEventRecord(h->ev_fork, st));
   RT_CUDA(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
-  void* ax = const_cast<void*>(device_alias(obs_xy_host));
-  void* ar = const_cast<void*>(device_alias(reward_host));
-  void* ad = const_cast<void*>(device_alias(done_host));
-  const bool dx = ax != nullptr, dr = ar != nullptr, dd = ad != nullptr;
-  const unsigned long long seq = ++h->host_seq;
-  k_results_to_host<<<(unsigned)h->d2h_ctas, 256, 0, h->aux>>>(
-      h->d_obs_xy, h->d_reward, h->d_done, n, static_cast<int32_t*>(dx ? ax : (void*)p_xy),
-      static_cast<int32_t*>(dr ? ar : (void*)p_rw), static_cast<uint8_t*>(dd ? ad : (void*)p_dn), h->dev.step_flags,
-      reinterpret_cast<unsigned*>(h->d_flag_or + 2), p_fl, const_cast<unsigned long long*>(p_seq), seq);
-  h->launches += 1;
-  RT_CUDA_LAUNCH_CHECK();
+  const bool dx = is_pinned_or_device(obs_xy_host), dr = is_pinned_or_device(reward_host),
+             dd = is_pinned_or_device(done_host);
+  unsigned char* xy_b = reinterpret_cast<unsigned char*>(obs_xy_host);
+  if (dx && dr && dd && reinterpret_cast<unsigned char*>(reward_host) == xy_b + n * 8 && done_host == xy_b + n * 12) {
+    // the caller's three buffers are one pinned block laid out like the device's: ONE copy
+    RT_CUDA(cudaMemcpyAsync(obs_xy_host, h->d_obs_xy, n * 13, cudaMemcpyDefault, h->aux));
+  } else if (!dx && !dr && !dd) {
+    RT_CUDA(cudaMemcpyAsync(p_xy, h->d_obs_xy, n * 13, cudaMemcpyDefault, h->aux));  // staging has the same layout
+  } else {
+    RT_CUDA(cudaMemcpyAsync(dx ? (void*)obs_xy_host : (void*)p_xy, h->d_obs_xy, n * 8, cudaMemcpyDefault, h->aux));
+    RT_CUDA(cudaMemcpyAsync(dr ? (void*)reward_host : (void*)p_rw, h->d_reward, n * 4, cudaMemcpyDefault, h->aux));
+    RT_CUDA(cudaMemcpyAsync(dd ? (void*)done_host : (void*)p_dn, h->d_done, n, cudaMemcpyDefault, h->aux));
+  }
+  // flags + sequence number, behind the results in stream order: when the number has landed, so has everything else
+  RT_CUDA(cudaMemcpyAsync(const_cast<int32_t*>(p_fl), h->dev.step_flags, 16, cudaMemcpyDeviceToHost, h->aux));
   if (obs_maps_dev) {
     rc = raster_or_patch(h, obs_maps_dev, st);
     if (rc != RT_OK) return rc;
   }
-  // Return when the step's results are in host memory: poll the sequence word the return kernel publishes last
-  // (no driver call on the wait).  The rasteriser keeps streaming on `st`: whatever the host does before its next
-  // call hides under it, and everything enqueued on `st` later is ordered behind it.
+  // Return when the step's results are in host memory: poll the sequence word (no driver call on the wait).  The
+  // rasteriser keeps streaming on `st`: whatever the host does before its next call hides under it, and everything
+  // enqueued on `st` later is ordered behind it.
   for (unsigned spins = 0; *p_seq != seq;) {
     rt_cpu_relax();
     if ((++spins & 0xfffffu) == 0 && cudaStreamQuery(h->aux) != cudaErrorNotReady) {  // finished or failed
       if (*p_seq == seq) break;
       RT_CUDA(cudaStreamSynchronize(h->aux));
       if (*p_seq != seq) {
-        rt_note_error_text("rt_env_step_host: result-return kernel finished without publishing its results");
+        rt_note_error_text("rt_env_step_host: the results' sequence number did not arrive");
         return RT_ERR_CUDA;
       }
     }
@@ -663,7 +641,7 @@ int rt_env_step_host(rt_env* h, const int32_t* actions_host, int32_t* obs_xy_hos
   if (!dx) std::memcpy(obs_xy_host, p_xy, n * 8);
   if (!dr) std::memcpy(reward_host, p_rw, n * 4);
   if (!dd) std::memcpy(done_host, p_dn, n);
-  if (*p_fl & RT_FLAG_BAD_ACTION) return RT_ERR_BAD_ACTION;
+  if (p_fl[seq & 1] & RT_FLAG_BAD_ACTION) return RT_ERR_BAD_ACTION;
   return RT_OK;
 }
 

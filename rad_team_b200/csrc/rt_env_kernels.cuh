@@ -63,7 +63,10 @@ struct EnvDev {
   int32_t* ep_return;  // [E][A]
   uint8_t* ep_done;    // [E][A]
   float* rollout;      // [T][E][A] readings sink, or nullptr
-  int32_t* step_flags; // one word: OR of the RT_FLAG_* that voided an env's step in the CURRENT launch
+  int32_t* step_flags; // host path, 16 B: word [host_seq & 1] = OR of the RT_FLAG_* that voided an env's step in THIS
+                       //   launch, [2..3] = host_seq of the last launch; a launch clears the word of the NEXT call
+                       //   (the other one), so no memset sits in front of a step
+  unsigned long long host_seq;  // sequence number of the rt_env_step_host call this launch belongs to
   int live_dense;      // 1: k_step keeps the dense visit / intensity maps current (dense / generic rasterisers); 0: cell
                        //    records + visited-cell records are the only copy, dense maps are materialised on request
   uint4* prev_cells;   // [E] the agents' cells BEFORE the last step (8 x uint16), for the incremental observation update
@@ -522,7 +525,7 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
     const int skip3 = s.skip[t];
     if (skip3) {
       atomicOr(&d.flags[e3], skip3);
-      atomicOr(d.step_flags, skip3);
+      atomicOr(d.step_flags + (d.host_seq & 1ull), skip3);
     } else {
       cp_async_wait_all();  // this thread's own copies: its row of the staged state is complete
       const unsigned char* row = reinterpret_cast<const unsigned char*>(s.own + (size_t)t * kOwnF4);
@@ -546,6 +549,10 @@ k_step(const EnvDev d, const int32_t* __restrict__ actions, int32_t* __restrict_
   extern __shared__ __align__(16) unsigned char smem_raw[];
   pdl_launch_dependents();
   pdl_wait();  // the rasteriser of the previous step still reads the records this kernel updates
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // host path bookkeeping (see EnvDev::step_flags)
+    d.step_flags[(d.host_seq + 1ull) & 1ull] = 0;
+    *reinterpret_cast<unsigned long long*>(d.step_flags + 2) = d.host_seq;
+  }
   step_tile(d, actions, obs_xy, reward, done, smem_raw);
 }
 

@@ -229,14 +229,35 @@ k_moments_partial(const float* __restrict__ x0, long long n0, int head, double* 
   long long i = (long long)blockIdx.x * kMomThreads + threadIdx.x;
   Shifted sh = {0.0, 0.0, 0.0, 0.0};
   if (i < n4) sh.k = (double)x[4 * i];
-  for (; i + (kMomUnroll - 1) * stride < n4; i += kMomUnroll * stride) {
-    float4 v[kMomUnroll];
+  // Software pipeline: the kMomUnroll loads of the NEXT round are issued before the current round is folded, so
+  // every thread keeps kMomUnroll 16-byte loads in flight whatever order the scheduler gives the folds (left to
+  // itself ptxas interleaved load / fold / load / fold: one load in flight per thread, 4.3 TB/s instead of 6).
+  // Two accumulator pairs halve the dependent fp64 chain; they are added once at the end (fixed order).
+  Shifted sb = {sh.k, 0.0, 0.0, 0.0};
+  float4 cur[kMomUnroll], nxt[kMomUnroll];
+  bool have = i + (kMomUnroll - 1) * stride < n4;
+  if (have) {
 #pragma unroll
-    for (int u = 0; u < kMomUnroll; ++u) v[u] = ld_stream_f4(x + 4 * (i + u * stride));
+    for (int u = 0; u < kMomUnroll; ++u) cur[u] = ld_stream_f4(x + 4 * (i + u * stride));
+  }
+  while (have) {
+    const long long j = i + kMomUnroll * stride;
+    const bool more = j + (kMomUnroll - 1) * stride < n4;
+    if (more) {
 #pragma unroll
-    for (int u = 0; u < kMomUnroll; ++u) fold_quad(sh, v[u]);
+      for (int u = 0; u < kMomUnroll; ++u) nxt[u] = ld_stream_f4(x + 4 * (j + u * stride));
+    }
+#pragma unroll
+    for (int u = 0; u < kMomUnroll; ++u) fold_quad((u & 1) ? sb : sh, cur[u]);
+#pragma unroll
+    for (int u = 0; u < kMomUnroll; ++u) cur[u] = nxt[u];
+    i = j;
+    have = more;
   }
   for (; i < n4; i += stride) fold_quad(sh, ld_stream_f4(x + 4 * i));
+  sh.s1 += sb.s1;
+  sh.s2 += sb.s2;
+  sh.n += sb.n;
   Mom acc = {0.0, 0.0, 0.0};
   if (sh.n > 0.0) {
     acc.n = sh.n;

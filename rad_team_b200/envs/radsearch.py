@@ -146,10 +146,12 @@ class BatchedRadSearchEnv:
 
     def _host_bufs(self):
         if self._h_xy is None:
-            t = self._torch
-            self._h_xy = t.zeros((self.E, self.A, 2), dtype=t.int32).pin_memory()
-            self._h_rw = t.zeros((self.E, self.A), dtype=t.int32).pin_memory()
-            self._h_dn = t.zeros((self.E, self.A), dtype=t.uint8).pin_memory()
+            # ONE pinned block laid out obs_xy | reward | done: rt_env_step_host then returns all three with one copy
+            t, n = self._torch, self.E * self.A
+            self._h_block = t.zeros(n * 13, dtype=t.uint8).pin_memory()
+            self._h_xy = self._h_block[:n * 8].view(t.int32).view(self.E, self.A, 2)
+            self._h_rw = self._h_block[n * 8:n * 12].view(t.int32).view(self.E, self.A)
+            self._h_dn = self._h_block[n * 12:].view(self.E, self.A)
         return self._h_xy, self._h_rw, self._h_dn
 
     def buffer(self, name: str):
