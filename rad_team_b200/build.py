@@ -27,6 +27,7 @@ NVCC_FLAGS = [
     "-fmad=false",
     "-Xcompiler", "-fPIC", "-shared",
     "-Xptxas", "-v",
+    "-ldl",  # header-only NVTX3 loads the profiler's injection library lazily
 ]
 
 

@@ -334,6 +334,7 @@ int rt_stats_allgather_merge(rt_comm* c, rt_moments* local, rt_moments* global, 
   }
   if (local->device != c->device || global->device != c->device) return RT_ERR_BAD_ARG;
   RtDeviceGuard on_device(c->device);
+  RtRange nvtx_range("rt_stats_allgather_merge");
   double *ls = local->state, *gs = global->state;
   CommDev d;
   d.rank = c->rank;

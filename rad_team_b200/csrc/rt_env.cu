@@ -53,6 +53,7 @@ struct rt_env {
   bool sparse = true;                       // RT_B200_RASTER=dense selects the dense (LSU) rasteriser
   int sparse_ctas = 24;                     // k_raster_sparse_lsu: CTAs (8 warp pipelines each) per SM in the grid (2 resident)
   bool sparse_lsu = true;                   // RT_B200_RASTER=sparse_tma selects the bulk-store variant
+  bool small_raster = false;                // L2-resident observation tensor: k_raster_small (RT_B200_RASTER=small forces it)
   bool pdl = true;                          // RT_B200_PDL=0: plain stream-ordered launches of k_step / the rasteriser
   int sparse_hints = 19;                    // bit 0/1: TMA variant L2 hints; bit 4: plain st.global (else .cs) in the LSU variant
 };
@@ -181,7 +182,10 @@ void launch_raster_vec(rt_env* h, float* obs_maps, cudaStream_t st) {
 int launch_raster(rt_env* h, float* obs_maps, cudaStream_t st) {
   const EnvDev& d = h->dev;
   h->last_maps = obs_maps;
-  if (h->sparse && h->sparse_lsu) {
+  if (h->sparse && h->small_raster) {
+    // small batch: warp per env, zeros streamed while k_step still runs, cells patched after it (k_raster_small)
+    RT_CUDA(launch_pdl(k_raster_small, (unsigned)((d.E + 7) / 8), 256u, (size_t)0, st, h->pdl, d, obs_maps));
+  } else if (h->sparse && h->sparse_lsu) {
     // visit-table lookups are rare here (a few dozen per env), so the table is read through L1 from global
     // memory: staging it in shared memory per CTA (+ a CTA barrier) was measured slower (profiles/r02a)
     const size_t smb = raster_sl_smem_bytes(d.cells, 0);
@@ -460,6 +464,12 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
                  { rt_env_destroy(h); });
     }
   }
+  // small batches (observation tensor well inside the 126 MB L2): the warp-per-env zero-then-patch rasteriser
+  h->small_raster = h->sparse && (cells & 3) == 0 && E * cells * 12 <= (size_t)64 << 20;
+  if (const char* ev = std::getenv("RT_B200_RASTER")) {
+    if (std::strcmp(ev, "small") == 0) h->small_raster = h->sparse && (cells & 3) == 0;
+    else if (std::strcmp(ev, "auto") != 0) h->small_raster = false;  // an explicit choice of another variant
+  }
   d.live_dense = h->sparse ? 0 : 1;
   RT_CUDA_OR(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking), { rt_env_destroy(h); });
   RT_CUDA_OR(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming), { rt_env_destroy(h); });
@@ -509,6 +519,7 @@ int rt_env_reset(rt_env* h, const uint8_t* mask_dev, int32_t* obs_xy_dev, float*
                  void* stream) {
   if (!h) return RT_ERR_BAD_ARG;
   RtDeviceGuard on_device(h->device);
+  RtRange nvtx_range("rt_env_reset");
   return launch_reset(h, mask_dev, obs_xy_dev, obs_maps_dev, (cudaStream_t)stream);
 }
 
@@ -516,6 +527,7 @@ int rt_env_step(rt_env* h, const int32_t* actions_dev, int32_t* obs_xy_dev, floa
                 int32_t* reward_dev, uint8_t* done_dev, void* stream) {
   if (!h || !actions_dev || !obs_xy_dev || !reward_dev || !done_dev) return RT_ERR_BAD_ARG;
   RtDeviceGuard on_device(h->device);
+  RtRange nvtx_range("rt_env_step");
   return launch_step(h, actions_dev, obs_xy_dev, obs_maps_dev, reward_dev, done_dev,
                      (cudaStream_t)stream);
 }
@@ -524,6 +536,7 @@ int rt_env_reset_host(rt_env* h, const uint8_t* mask_host, int32_t* obs_xy_host,
                       void* stream) {
   if (!h) return RT_ERR_BAD_ARG;
   RtDeviceGuard on_device(h->device);
+  RtRange nvtx_range("rt_env_reset_host");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t E = (size_t)h->dev.E, A = (size_t)h->dev.A;
   const uint8_t* mask_dev = nullptr;
@@ -572,6 +585,7 @@ int rt_env_step_host(rt_env* h, const int32_t* actions_host, int32_t* obs_xy_hos
                      uint8_t* done_host, float* obs_maps_dev, void* stream) {
   if (!h || !actions_host || !obs_xy_host || !reward_host || !done_host) return RT_ERR_BAD_ARG;
   RtDeviceGuard on_device(h->device);
+  RtRange nvtx_range("rt_env_step_host");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = (size_t)h->dev.E * h->dev.A;
   unsigned char* p_act = h->pinned;
@@ -648,6 +662,7 @@ int rt_env_step_host(rt_env* h, const int32_t* actions_host, int32_t* obs_xy_hos
 int rt_env_rasterize(rt_env* h, float* obs_maps_dev, void* stream) {
   if (!h || !obs_maps_dev) return RT_ERR_BAD_ARG;
   RtDeviceGuard on_device(h->device);
+  RtRange nvtx_range("rt_env_rasterize");
   return launch_raster(h, obs_maps_dev, (cudaStream_t)stream);
 }
 
@@ -674,6 +689,7 @@ int rt_env_set_rollout(rt_env* h, float* readings_dev) {
 int rt_env_episode_stats(rt_env* h, double* stats_dev, void* stream) {
   if (!h || !stats_dev) return RT_ERR_BAD_ARG;
   RtDeviceGuard on_device(h->device);
+  RtRange nvtx_range("rt_env_episode_stats");
   cudaStream_t st = (cudaStream_t)stream;
   RT_CUDA(cudaMemsetAsync(stats_dev, 0, 3 * sizeof(double), st));
   long long blocks = ((long long)h->dev.E * h->dev.A + 255) / 256;

@@ -1043,6 +1043,63 @@ k_raster_sparse_lsu(const EnvDev d, float* __restrict__ out, int plain_stores) {
   }
 }
 
+// K3 for SMALL batches (observation tensor L2-resident, e.g. BASELINE configs[1]: 4,096 envs = 50 MB).  The tile
+// rasterisers above need 12 KB of shared memory per warp (2 CTAs per SM): 4,096 envs are 1.7 waves of a kernel whose
+// every wave costs a full record-load latency, behind a k_step that is itself one latency chain.  Here every env
+// gets its own warp and NO shared memory, so all warps are resident at once, and the work is split around the
+// programmatic-dependent-launch wait:
+//   before the wait (while k_step still runs — nothing here depends on it): the warp streams the env's 12 KB of
+//     zeros with coalesced 16-byte stores.  The tensor's previous readers were launched before k_step and have exited;
+//   after the wait: it loads the env's record list and patches the few non-zero cells (agents, visited cells) with
+//     4-byte stores into lines it has just written — they are still in the L2.  __syncwarp orders the two phases.
+__global__ void __launch_bounds__(256)
+k_raster_small(const EnvDev d, float* __restrict__ out) {
+  const int cells = d.cells, lane = threadIdx.x & 31;
+  const long long e = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  pdl_launch_dependents();
+  if (e >= d.E) {
+    pdl_wait();
+    return;
+  }
+  float* o = out + (size_t)e * 3 * cells;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int n4 = (cells * 3) >> 2;
+  for (int i = lane; i < n4; i += 32) st_plain_f4(o + 4 * i, z4);
+  pdl_wait();  // k_step's records are complete and visible from here on
+  const uint2* rec = d.vrec + (size_t)e * d.rec_stride;
+  const uint2 h0 = rec[0];
+  const int nv = (int)h0.x;
+  uint2 r[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {  // slots lane, lane + 32, ...: header, agent cells, the first 125 records
+    const int j = lane + 32 * m;
+    r[m] = (j < 3 + nv && j < d.rec_stride) ? rec[j] : make_uint2(0u, 0u);
+  }
+  __syncwarp();  // the zeros of every lane are ordered before any lane's patch
+  const uint32_t w1x = __shfl_sync(0xffffffffu, r[0].x, 1), w1y = __shfl_sync(0xffffffffu, r[0].y, 1);
+  const uint32_t w2x = __shfl_sync(0xffffffffu, r[0].x, 2), w2y = __shfl_sync(0xffffffffu, r[0].y, 2);
+  if (lane < RT_MAX_AGENTS) {
+    const uint32_t word = lane < 2 ? w1x : (lane < 4 ? w1y : (lane < 6 ? w2x : w2y));
+    const int acell = (int)((lane & 1) ? (word >> 16) : (word & 0xffffu));
+    if (acell != 0xffff) o[acell] = 1.0f;
+  }
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int j = lane + 32 * m;
+    if (j >= 3 && j - 3 < nv) {
+      const int cell = (int)(r[m].x & 0xffffu);
+      o[cells + cell] = __uint_as_float(r[m].y);
+      o[2 * cells + cell] = d.lut[r[m].x >> 16];
+    }
+  }
+  for (int j = 128 + lane; j - 3 < nv; j += 32) {  // rare: more than 125 visited cells
+    const uint2 q = rec[j];
+    const int cell = (int)(q.x & 0xffffu);
+    o[cells + cell] = __uint_as_float(q.y);
+    o[2 * cells + cell] = d.lut[q.x >> 16];
+  }
+}
+
 // K3, incremental form (opt-in, rt_env_set_incremental): when the caller hands back the SAME tensor that
 // holds this env's previous observation, a step changes at most 2A cells per env — the agents' old cells
 // lose their location mark, the new cells get mark, intensity and visit value.  One thread per env.

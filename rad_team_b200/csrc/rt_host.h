@@ -32,6 +32,25 @@ struct rt_moments {
   int max_blocks = 0;
 };
 
+// NVTX ranges around the C-ABI entry points (rt_env_step / rasterize / reset, rollout close) so that an nsys timeline
+// reads in the library's own terms.  Header-only NVTX3: a no-op costing a few nanoseconds unless a profiler is attached.
+#if defined(__has_include)
+#if __has_include(<nvtx3/nvToolsExt.h>)
+#include <nvtx3/nvToolsExt.h>
+#define RT_HAVE_NVTX 1
+#endif
+#endif
+struct RtRange {
+#ifdef RT_HAVE_NVTX
+  explicit RtRange(const char* name) { nvtxRangePushA(name); }
+  ~RtRange() { nvtxRangePop(); }
+#else
+  explicit RtRange(const char*) {}
+#endif
+  RtRange(const RtRange&) = delete;
+  RtRange& operator=(const RtRange&) = delete;
+};
+
 #define RT_CUDA(call)                         \
   do {                                        \
     cudaError_t rt_e_ = (call);               \

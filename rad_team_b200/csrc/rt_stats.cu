@@ -439,6 +439,7 @@ int rt_moments_reset(rt_moments* m, void* stream) {
 int rt_moments_update(rt_moments* m, const float* x_dev, int64_t n, void* stream) {
   if (!m || !x_dev || n < 0) return RT_ERR_BAD_ARG;
   RtDeviceGuard on_device(m->device);
+  RtRange nvtx_range("rt_moments_update");
   if (((uintptr_t)x_dev & 3) != 0) return RT_ERR_BAD_ARG;  // not even a float boundary
   if (n == 0) return RT_OK;
   // any contiguous float32 view works (a row readings[t] of a [T, E, A] buffer, x[1:]): up to three readings in
@@ -457,6 +458,7 @@ int rt_moments_update(rt_moments* m, const float* x_dev, int64_t n, void* stream
 int rt_moments_standardize(rt_moments* m, const float* x_dev, float* out_dev, int64_t n, void* stream) {
   if (!m || !x_dev || !out_dev || n < 0) return RT_ERR_BAD_ARG;
   RtDeviceGuard on_device(m->device);
+  RtRange nvtx_range("rt_moments_standardize");
   if ((((uintptr_t)x_dev | (uintptr_t)out_dev) & 3) != 0) return RT_ERR_BAD_ARG;
   if (n == 0) return RT_OK;
   long long blocks = ((n >> 2) + 255) / 256;

@@ -284,13 +284,16 @@ def test_sparse_and_dense_rasterisers_agree(monkeypatch, kw):
     from rad_team_b200.envs import BatchedRadSearchEnv
 
     full = dict(O.DEFAULTS); full.update(kw)
-    sparse = BatchedRadSearchEnv(**full)
+    small = BatchedRadSearchEnv(**full)   # default at this size: k_raster_small (warp per env, zeros then patch)
+    monkeypatch.setenv("RT_B200_RASTER", "sparse_lsu")
+    sparse = BatchedRadSearchEnv(**full)  # the large-batch default, forced
     monkeypatch.setenv("RT_B200_RASTER", "dense")
     monkeypatch.setenv("RT_B200_EPB", "16")
     monkeypatch.setenv("RT_B200_RASTER_UNROLL", "4")
     dense = BatchedRadSearchEnv(**full)
     monkeypatch.delenv("RT_B200_RASTER"); monkeypatch.delenv("RT_B200_EPB"); monkeypatch.delenv("RT_B200_RASTER_UNROLL")
     monkeypatch.setenv("RT_B200_SPARSE_CTAS", "1")
+    monkeypatch.setenv("RT_B200_RASTER", "sparse_lsu")
     split = BatchedRadSearchEnv(**full)
     monkeypatch.setenv("RT_B200_RASTER", "sparse_tma")
     tma = BatchedRadSearchEnv(**full)
@@ -298,7 +301,7 @@ def test_sparse_and_dense_rasterisers_agree(monkeypatch, kw):
     orc = O.OracleEnv(**full)
     E, A, T = full["n_envs"], full["n_agents"], full["max_steps"]
     rng = np.random.default_rng(kw["seed"])
-    for env in (sparse, dense, split, tma):
+    for env in (small, sparse, dense, split, tma):
         env.reset()
     _, m_o = orc.reset()
     assert np.array_equal(sparse.obs_maps.cpu().numpy(), m_o) and torch.equal(sparse.obs_maps, dense.obs_maps)
@@ -307,9 +310,10 @@ def test_sparse_and_dense_rasterisers_agree(monkeypatch, kw):
         if t % 3 == 0:  # drive agents along long straight paths so that many distinct cells get visited
             a_np[:] = 1 + (t // 30) % 4
         act = torch.as_tensor(a_np, device=sparse.device)
-        sparse.step(act); dense.step(act); tma.step(act)
+        small.step(act); sparse.step(act); dense.step(act); tma.step(act)
         split.step(act, rasterize=False); split.rasterize()
         _, m_o, _, _ = orc.step(a_np)
+        assert torch.equal(sparse.obs_maps, small.obs_maps), t
         assert torch.equal(sparse.obs_maps, dense.obs_maps), t
         assert torch.equal(sparse.obs_maps, split.obs_maps), t
         assert torch.equal(sparse.obs_maps, tma.obs_maps), t
