@@ -306,8 +306,11 @@ def phase_plan(K: int, W: int):
     return warm, t0
 
 
-def measure(cx: Ctx, w, E, base, K, W, full: bool, e2e_steps: int = 0):
-    """Device-resident loop + host-buffer loop of one workload on this rank's shard.  Returns a dict."""
+def measure(cx: Ctx, w, E, base, K, W, full: bool, e2e_steps: int = 0, graph: bool = False):
+    """Device-resident loop + host-buffer loop of one workload on this rank's shard.  Returns a dict.
+    graph=True (K a multiple of 120): the device-resident loop is ONE captured CUDA graph of a whole episode — 120
+    steps, the rollout close and the reset — replayed K / 120 times: for small batches the Python loop cannot issue
+    two launches per ~15 us step, and the device-resident number would measure the host."""
     torch, dev, world = cx.torch, cx.dev, cx.world
     from rad_team_b200.envs import BatchedRadSearchEnv
     from rad_team_b200.math_utils import RunningMoments
@@ -365,6 +368,7 @@ def measure(cx: Ctx, w, E, base, K, W, full: bool, e2e_steps: int = 0):
         if st["tick"] == T:
             close_rollout(False, timed)
 
+    graph = graph and K % T == 0
     warm, t0 = phase_plan(K, W)
     # ---- device-resident throughput ("value") -------------------------------------------------
     env.reset()
@@ -372,16 +376,47 @@ def measure(cx: Ctx, w, E, base, K, W, full: bool, e2e_steps: int = 0):
     for _ in range(warm):
         dev_step()
     assert st["tick"] == t0
-    cx.barrier()
-    l0, x0, c0 = env.launches, st["extra"], st["closes"]
-    ev0, ev1 = ev(), ev()
-    ev0.record()
-    for i in range(K):
-        dev_step(probe=(i % 8 == 3), timed=True)  # every 8th step also times its two kernels, live, on this stream
-    ev1.record()
-    cx.barrier()
-    ms_total = cx.max_over_ranks(ev0.elapsed_time(ev1))
-    launches = (env.launches - l0) + (st["extra"] - x0)
+    if graph:
+        while st["tick"] != 0:
+            dev_step()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            l0, x0 = env.launches, st["extra"]
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):   # 120 x (k_step + rasteriser), close (moments, stats, exchange), reset
+                for _ in range(T):
+                    dev_step()
+            per_episode = (env.launches - l0) + (st["extra"] - x0)
+            g.replay()                               # the capture executed nothing: run the episode once
+            side.synchronize()
+            cx.barrier()
+            c0 = st["closes"]
+            ev0, ev1 = ev(), ev()
+            ev0.record()
+            for _ in range(K // T):
+                g.replay()
+            ev1.record()
+            side.synchronize()
+        torch.cuda.current_stream().wait_stream(side)
+        st["closes"] += K // T                       # the capture counted one close (= the warm replay); add the timed ones
+        cx.barrier()
+        ms_total = cx.max_over_ranks(ev0.elapsed_time(ev1))
+        launches = per_episode * (K // T)
+        for i in range(16):                          # kernel samples, eagerly, right after the timed region
+            dev_step(probe=True)
+        torch.cuda.synchronize()
+    else:
+        cx.barrier()
+        l0, x0, c0 = env.launches, st["extra"], st["closes"]
+        ev0, ev1 = ev(), ev()
+        ev0.record()
+        for i in range(K):
+            dev_step(probe=(i % 8 == 3), timed=True)  # every 8th step also times its two kernels, live, on this stream
+        ev1.record()
+        cx.barrier()
+        ms_total = cx.max_over_ranks(ev0.elapsed_time(ev1))
+        launches = (env.launches - l0) + (st["extra"] - x0)
     closes_dev = st["closes"] - c0
     n_probe_c = len(probes)
     kstep_ms = sum(e[0].elapsed_time(e[1]) for e in probes) / max(1, n_probe_c)
@@ -392,7 +427,9 @@ def measure(cx: Ctx, w, E, base, K, W, full: bool, e2e_steps: int = 0):
 
     out = {"E": E, "ms_total": ms_total, "ms_per_step": ms_total / K, "launches": int(launches),
            "closes_dev": closes_dev, "close_ms": close_ms, "exchange_ms": exch_ms, "kstep_ms": kstep_ms,
-           "raster_compressible_ms": raster_c_ms, "probe_samples": n_probe_c}
+           "raster_compressible_ms": raster_c_ms, "probe_samples": n_probe_c,
+           "mode": "one CUDA graph per episode (120 steps + rollout close + reset), replayed" if graph
+                   else "eager launches from the Python loop"}
 
     if full:
         # ---- a longer window of the same loop: whole episodes, so the close is amortised as in production -------
@@ -402,10 +439,19 @@ def measure(cx: Ctx, w, E, base, K, W, full: bool, e2e_steps: int = 0):
         cx.barrier()
         la, lb = ev(), ev()
         c1 = st["closes"]
-        la.record()
-        for _ in range(n_long):
-            dev_step()
-        lb.record()
+        if graph:
+            with torch.cuda.stream(side):
+                la.record()
+                for _ in range(n_long // T):
+                    g.replay()
+                lb.record()
+                side.synchronize()
+            st["closes"] += n_long // T
+        else:
+            la.record()
+            for _ in range(n_long):
+                dev_step()
+            lb.record()
         cx.barrier()
         out["long"] = {"steps": n_long, "ms_per_step": cx.max_over_ranks(la.elapsed_time(lb)) / n_long,
                        "closes": st["closes"] - c1}
@@ -536,7 +582,8 @@ def run_ours(args, rank, world, local_rank):
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    m = measure(cx, w, E, base, K, W, full=True, e2e_steps=args.e2e_steps)
+    use_graph = args.graph == "on" or (args.graph == "auto" and wname == "c2")
+    m = measure(cx, w, E, base, K, W, full=True, e2e_steps=args.e2e_steps, graph=use_graph)
     clocks = sampler.stop()
     env, rollout = m.pop("env"), m.pop("rollout")
 
@@ -641,14 +688,14 @@ def run_ours(args, rank, world, local_rank):
                 "raster_ms": s["raster_compressible_ms"]}
         if world == 1 and wname == "c3":
             w2 = WORKLOADS["c2"]
-            K2s = max(K, 1200)
-            s = measure(cx, w2, w2["envs"], 0, K2s, W, full=False, e2e_steps=0)
+            K2s = -(-max(K, 1200) // T_EPISODE) * T_EPISODE
+            s = measure(cx, w2, w2["envs"], 0, K2s, W, full=False, e2e_steps=0, graph=True)
             s.pop("env"), s.pop("rollout")
             secondary["c2"] = {
                 "workload": w2["name"], "steps": K2s, "value": s["total_agents"] * K2s / (s["ms_total"] * 1e-3),
                 "ms_per_step": s["ms_per_step"], "e2e_value": s["total_agents"] * s["e2e_steps"] / s["e2e_s"],
                 "rollout_closes_timed": s["closes_dev"], "merge_check": s["merge_check"], "k_step_ms": s["kstep_ms"],
-                "raster_ms": s["raster_compressible_ms"],
+                "raster_ms": s["raster_compressible_ms"], "mode": s["mode"],
                 "regime": "L2-resident (50 MB observation tensor): launch / latency bound, not HBM"}
             torch.cuda.empty_cache()
 
@@ -679,6 +726,7 @@ def run_ours(args, rank, world, local_rank):
                        "rollout_close": "after tick 119: batch Welford moments + episode stats + exchange ("
                                         + exchange.backend + (" transport, %d ranks" % world) + ") + reset",
                        "arithmetic": "fp64 physics/statistics, fp32 geometry and maps, int32 indices/counts",
+                       "device_loop": m["mode"],
                        "cores_of_rank0": None if cores is None else len(cores)},
             "rollout_closes_timed": m["closes_dev"], "close_ms": mean_or_none(m["close_ms"]),
             "allgather_merge_ms": mean_or_none(m["exchange_ms"]),
@@ -748,6 +796,8 @@ def main():
                     help="default: c3 at N = 1, c4 (strong scaling, BASELINE configs[3]) at N > 1")
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"])
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="device-resident loop as one CUDA graph per episode (auto: c2 only; needs steps % 120 == 0)")
     ap.add_argument("--ref-envs", type=int, default=4096, help="envs in the CPU sample")
     ap.add_argument("--ref-seconds", type=float, default=1.0, help="--impl reference: minimum timed wall clock")
     ap.add_argument("--ref-py-seconds", type=float, default=2.0, help="per leg of the Python-reference timing")

@@ -430,6 +430,12 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
   if (epb > 32) epb = 32;  // measured: 32 envs per CTA beats 64 and 16 at c3 (profiles/r01m)
   while (epb > 8 && (cfg->n_envs + epb - 1) / epb < 2 * h->n_sm) epb >>= 1;
   if (epb * cfg->n_agents < 32) epb = (32 + cfg->n_agents - 1) / cfg->n_agents;
+  // Small batches (configs[1]: 4,096 x 1) are one latency chain per warp and leave most SMs idle: a warp runs the
+  // UNION of its lanes' sampler passes and bucket hops, so fewer envs per warp shorten the chain — until the number
+  // of CTAs itself costs more (measured at c2, CUDA-graph loop, envs per CTA -> us per step: 32 15.1, 16 14.6,
+  // 8 13.8, 4 13.2, 2 17.8, 1 19.2; profiles/r2g_*): about a thousand CTAs.
+  if ((long long)cfg->n_envs * cfg->n_agents <= 16384)
+    epb = std::min(32, std::max(1, (cfg->n_envs + 1023) / 1024));
   h->epb = epb;
   if (const char* ev = std::getenv("RT_B200_EPB")) {  // tuning knob: envs per CTA of the step kernels
     const int v = std::atoi(ev);

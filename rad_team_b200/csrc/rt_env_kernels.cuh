@@ -547,8 +547,12 @@ __global__ void __launch_bounds__(192, RT_STEP_MIN_CTAS)
 k_step(const EnvDev d, const int32_t* __restrict__ actions, int32_t* __restrict__ obs_xy,
        int32_t* __restrict__ reward, uint8_t* __restrict__ done) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  pdl_launch_dependents();
+  // Wait FIRST, then let the dependent kernel (this step's rasteriser) start: its CTAs may then assume that everything
+  // in front of k_step in the stream — the previous step's rasteriser, the consumer that read the observation tensor —
+  // has completed, which is what allows k_raster_small to write its zeros before its own wait.  (Triggering before the
+  // wait would let rasteriser t+1 start while rasteriser t is still patching the same tensor.)
   pdl_wait();  // the rasteriser of the previous step still reads the records this kernel updates
+  pdl_launch_dependents();
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // host path bookkeeping (see EnvDev::step_flags)
     d.step_flags[(d.host_seq + 1ull) & 1ull] = 0;
     *reinterpret_cast<unsigned long long*>(d.step_flags + 2) = d.host_seq;

@@ -346,3 +346,46 @@ class BatchedRadSearchEnv:
         with self._on_device():
             _lib.check(self._L.rt_env_rasterize(self._h, mptr, self._stream()), "rt_env_rasterize")
         return maps
+
+    def render(self, env_index: int = 0, window_size: int = 512, out_maps=None):
+        """``rgb_array`` frame of ONE env built from the DEVICE maps (the reference draws its
+        single agent with pygame, simple_gridworld.py:197-263): the observation tensor's own channels — intensity
+        in red, visits in green, agent cells in blue — plus the source cell (the reference's red target square) and
+        the obstruction rectangles, upsampled with nearest-neighbour to ``window_size`` pixels.  Row 0 of the frame
+        is the TOP of the world (y grows upward, as in the reference's ``ActionDirectionMap``).  Returns a uint8
+        NumPy array [window_size, window_size, 3]; only that one frame crosses PCIe."""
+        t = self._torch
+        maps = self.obs_maps if out_maps is None else out_maps
+        _lib.require(maps is not None, "render needs the observation tensor (alloc_maps=True or out_maps=...)")
+        _lib.require(0 <= env_index < self.E, "env_index out of range")
+        G = self.G
+        m = maps.view(self.E, 3, G, G)[env_index]                     # [3, G, G], map[row = y][col = x]
+        inten = m[1].clamp(0, 1)
+        visit = m[2].clamp(0, 1)
+        img = t.ones((3, G, G), dtype=t.float32, device=maps.device)
+        img[1] -= 0.8 * inten                                         # intensity: white -> red
+        img[2] -= 0.8 * inten
+        img[0] -= 0.5 * visit * (1 - inten)                           # visited, low intensity: towards green
+        img[2] -= 0.5 * visit * (1 - inten)
+        # obstructions: grey cells
+        n_poly = int(self.buffer("N_POLY")[env_index].item())
+        edges = self.buffer("EDGES")[env_index]
+        for p in range(n_poly):
+            e = edges[4 * p:4 * p + 4]
+            x0, x1 = int(e[:, [0, 2]].min().item()), int(e[:, [0, 2]].max().item())
+            y0, y1 = int(e[:, [1, 3]].min().item()), int(e[:, [1, 3]].max().item())
+            if x1 > x0 and y1 > y0:
+                img[:, y0:y1, x0:x1] = 0.45
+        sx, sy = (int(v) for v in self.buffer("SRC_XY")[env_index].tolist())
+        img[:, sy, sx] = t.tensor([1.0, 0.0, 0.0], device=maps.device)   # the source: the reference's red target
+        agents = m[0] > 0.5
+        img[0][agents], img[1][agents], img[2][agents] = 0.0, 0.0, 1.0  # agents: the reference's blue
+        img = img.flip(1)                                             # y up
+        scale = max(1, window_size // G)
+        img = img.repeat_interleave(scale, 1).repeat_interleave(scale, 2)
+        frame = t.zeros((3, window_size, window_size), dtype=t.float32, device=maps.device)
+        h = min(window_size, img.shape[1])
+        frame[:, :h, :h] = img[:, :h, :h]
+        frame[:, ::scale, :] = 0.0                                    # grid lines
+        frame[:, :, ::scale] = 0.0
+        return (frame.permute(1, 2, 0) * 255).round().to(t.uint8).cpu().numpy()

@@ -349,3 +349,25 @@ def test_vector_env_adapter_autoreset_and_shapes():
     with pytest.raises(ValueError, match="is not a valid Action"):
         venv.step(np.zeros((64, 2), np.int64))
     venv.close()
+
+
+@pytest.mark.gpu
+def test_batched_env_renders_an_rgb_frame_from_the_device_maps():
+    import torch
+    from rad_team_b200.envs import BatchedRadSearchEnv
+
+    env = BatchedRadSearchEnv(n_envs=4, n_agents=2, grid=16, max_steps=30, poly_min=1, poly_max=3, seed=5)
+    env.reset()
+    for t in range(6):
+        env.step(torch.full((4, 2), 1 + t % 4, dtype=torch.int32, device=env.device))
+    frame = env.render(env_index=2, window_size=512)
+    assert frame.shape == (512, 512, 3) and frame.dtype == np.uint8
+    scale = 512 // 16
+    xy = env.obs_xy.cpu().numpy()[2]
+    src = env.buffer("SRC_XY").cpu().numpy()[2]
+    for (x, y) in xy:  # agents are blue; row 0 of the frame is the top of the world
+        px = frame[(15 - y) * scale + scale // 2, x * scale + scale // 2]
+        assert tuple(px) == (0, 0, 255), (x, y, px)
+    if not any((src == a).all() for a in xy):
+        assert tuple(frame[(15 - src[1]) * scale + scale // 2, src[0] * scale + scale // 2]) == (255, 0, 0)
+    assert (frame[0, :, :] == 0).all() and (frame[:, 0, :] == 0).all()  # grid lines
