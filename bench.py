@@ -687,6 +687,20 @@ def run_ours(args, rank, world, local_rank):
                 "rollout_closes_timed": s["closes_dev"], "merge_check": s["merge_check"], "k_step_ms": s["kstep_ms"],
                 "raster_ms": s["raster_compressible_ms"]}
         if world == 1 and wname == "c3":
+            # the strong-scaling base of configs[3]: all 1,048,576 envs on ONE GPU (43 GB of state + 12.9 GB of maps)
+            w4 = WORKLOADS["c4"]
+            try:
+                s = measure(cx, w4, w4["envs"], 0, K, W, full=False, e2e_steps=min(K, 120))
+                s.pop("env"), s.pop("rollout")
+                secondary["c4_one_gpu"] = {
+                    "workload": w4["name"], "value": s["total_agents"] * K / (s["ms_total"] * 1e-3),
+                    "ms_per_step": s["ms_per_step"], "e2e_value": s["total_agents"] * s["e2e_steps"] / s["e2e_s"],
+                    "rollout_closes_timed": s["closes_dev"], "merge_check": s["merge_check"],
+                    "k_step_ms": s["kstep_ms"], "raster_ms": s["raster_compressible_ms"],
+                    "what": "divide the N-GPU c4 `value` by N x this for the strong-scaling efficiency of configs[3]"}
+            except Exception as exc:  # e.g. a smaller device: the headline must not die on a secondary figure
+                secondary["c4_one_gpu"] = {"error": f"{type(exc).__name__}: {exc}"}
+            torch.cuda.empty_cache()
             w2 = WORKLOADS["c2"]
             K2s = -(-max(K, 1200) // T_EPISODE) * T_EPISODE
             s = measure(cx, w2, w2["envs"], 0, K2s, W, full=False, e2e_steps=0, graph=True)

@@ -46,6 +46,7 @@ struct rt_env {
   cudaStream_t aux = nullptr;  // host path: results travel back here while the rasteriser streams
   cudaEvent_t ev_fork = nullptr;
   unsigned long long host_seq = 0;   // host path: results of call k have landed when the pinned sequence word reads k
+  size_t zc_out_bytes = 256 << 10;   // host path: results up to this size are stored by k_step itself (RT_B200_ZC_OUT_KB)
   int raster_ctas = 32, raster_unroll = 2;  // dense rasteriser: CTAs per SM (grid cap), chunks in flight per thread
   bool incremental = false;                 // rt_env_set_incremental: patch the caller's tensor when it is the same as last time
   const float* last_maps = nullptr;         // tensor that holds this env's latest observation
@@ -228,9 +229,13 @@ int raster_or_patch(rt_env* h, float* obs_maps, cudaStream_t st) {
 }
 
 int launch_step(rt_env* h, const int32_t* actions, int32_t* obs_xy, float* obs_maps, int32_t* reward,
-                uint8_t* done, cudaStream_t st, bool raster_follows = false) {
+                uint8_t* done, cudaStream_t st, bool raster_follows = false, bool publish_to_host = false) {
   EnvDev d = h->dev;
   d.host_seq = h->host_seq;
+  if (publish_to_host) {  // small-batch host path: the kernel itself returns flag word and sequence number
+    d.host_flag_out = static_cast<volatile int32_t*>(const_cast<void*>(device_alias(h->pinned + h->pinned_bytes - 16)));
+    d.host_seq_out = static_cast<volatile unsigned long long*>(const_cast<void*>(device_alias(h->pinned + h->pinned_bytes - 8)));
+  }
   const int epb = h->epb;
   const unsigned blocks = (unsigned)((d.E + epb - 1) / epb);
   RT_CUDA(launch_pdl(k_step, blocks, (unsigned)(epb * d.A), step_smem_bytes(epb, d.A), st, h->pdl, d, actions, obs_xy,
@@ -393,6 +398,9 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
   d.rollout = nullptr;
   d.step_flags = h->d_flag_or + 4;  // {flags of odd calls, of even calls, sequence number (8 B)}, 16-byte aligned
   d.host_seq = 0;
+  d.host_flag_out = nullptr;
+  d.host_seq_out = nullptr;
+  d.cta_counter = reinterpret_cast<unsigned*>(h->d_flag_or + 2);
   d.prev_cells = (uint4*)(base + o_prev);
   d.inj = nullptr;
   d.inj_k = 0;
@@ -442,6 +450,7 @@ int rt_env_create(const rt_env_cfg* cfg, rt_env** out) {
     if (v >= 1 && v * cfg->n_agents <= 192) h->epb = v;
   }
   if (const char* ev = std::getenv("RT_B200_ZEROCOPY")) h->zerocopy = std::atoi(ev) != 0;
+  if (const char* ev = std::getenv("RT_B200_ZC_OUT_KB")) h->zc_out_bytes = (size_t)std::max(0, std::atoi(ev)) << 10;
 
   if (const char* ev = std::getenv("RT_B200_RASTER_CTAS")) h->raster_ctas = std::max(1, std::atoi(ev));
   if (const char* ev = std::getenv("RT_B200_RASTER_UNROLL")) h->raster_unroll = std::max(1, std::atoi(ev));
@@ -620,12 +629,47 @@ int rt_env_step_host(rt_env* h, const int32_t* actions_host, int32_t* obs_xy_hos
   // k_step (it stamps this call's sequence number next to the flag word and clears the word of the NEXT call: no
   // memset), then the small results travel back on the auxiliary stream WHILE the rasteriser streams on `st`.
   const unsigned long long seq = ++h->host_seq;
+  const bool dx = is_pinned_or_device(obs_xy_host), dr = is_pinned_or_device(reward_host),
+             dd = is_pinned_or_device(done_host);
+  // Small batches: no copy engine at all.  k_step stores obs_xy / reward / done straight into mapped host memory (the
+  // caller's pinned buffers, or the handle's staging) and its last CTA publishes the flag word and the sequence
+  // number: two launches and a poll per step.  (A copy-engine request costs ~6 us of latency whatever its size —
+  // profiles/r2b_k4b_probe: 16 bytes 6.2 us — so for a 53 KB result it IS the step; above ~256 KB the copy engine's
+  // bandwidth wins and keeps the stores off k_step's critical path.)
+  if (h->zerocopy && n * 13 <= h->zc_out_bytes) {
+    int32_t* o_xy = static_cast<int32_t*>(const_cast<void*>(device_alias(dx ? (void*)obs_xy_host : (void*)p_xy)));
+    int32_t* o_rw = static_cast<int32_t*>(const_cast<void*>(device_alias(dr ? (void*)reward_host : (void*)p_rw)));
+    uint8_t* o_dn = static_cast<uint8_t*>(const_cast<void*>(device_alias(dd ? (void*)done_host : (void*)p_dn)));
+    if (o_xy && o_rw && o_dn) {
+      int rc = launch_step(h, actions_dev, o_xy, nullptr, o_rw, o_dn, st, obs_maps_dev != nullptr, true);
+      if (rc != RT_OK) return rc;
+      if (obs_maps_dev) {
+        rc = raster_or_patch(h, obs_maps_dev, st);
+        if (rc != RT_OK) return rc;
+      }
+      for (unsigned spins = 0; *p_seq != seq;) {
+        rt_cpu_relax();
+        if ((++spins & 0xfffffu) == 0 && cudaStreamQuery(st) != cudaErrorNotReady) {
+          if (*p_seq == seq) break;
+          RT_CUDA(cudaStreamSynchronize(st));
+          if (*p_seq != seq) {
+            rt_note_error_text("rt_env_step_host: the results' sequence number did not arrive");
+            return RT_ERR_CUDA;
+          }
+        }
+      }
+      std::atomic_thread_fence(std::memory_order_acquire);
+      if (!dx) std::memcpy(obs_xy_host, p_xy, n * 8);
+      if (!dr) std::memcpy(reward_host, p_rw, n * 4);
+      if (!dd) std::memcpy(done_host, p_dn, n);
+      if (p_fl[seq & 1] & RT_FLAG_BAD_ACTION) return RT_ERR_BAD_ACTION;
+      return RT_OK;
+    }
+  }
   int rc = launch_step(h, actions_dev, h->d_obs_xy, nullptr, h->d_reward, h->d_done, st, obs_maps_dev != nullptr);
   if (rc != RT_OK) return rc;
   RT_CUDA(cudaEventRecord(h->ev_fork, st));
   RT_CUDA(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
-  const bool dx = is_pinned_or_device(obs_xy_host), dr = is_pinned_or_device(reward_host),
-             dd = is_pinned_or_device(done_host);
   unsigned char* xy_b = reinterpret_cast<unsigned char*>(obs_xy_host);
   if (dx && dr && dd && reinterpret_cast<unsigned char*>(reward_host) == xy_b + n * 8 && done_host == xy_b + n * 12) {
     // the caller's three buffers are one pinned block laid out like the device's: ONE copy

@@ -67,6 +67,11 @@ struct EnvDev {
                        //   launch, [2..3] = host_seq of the last launch; a launch clears the word of the NEXT call
                        //   (the other one), so no memset sits in front of a step
   unsigned long long host_seq;  // sequence number of the rt_env_step_host call this launch belongs to
+  // small-batch host path: k_step writes obs_xy / reward / done straight into mapped host memory and its LAST CTA
+  // publishes {flag word, sequence number} there (nullptr: results are copied back by the copy engine instead)
+  volatile int32_t* host_flag_out;
+  volatile unsigned long long* host_seq_out;
+  unsigned* cta_counter;
   int live_dense;      // 1: k_step keeps the dense visit / intensity maps current (dense / generic rasterisers); 0: cell
                        //    records + visited-cell records are the only copy, dense maps are materialised on request
   uint4* prev_cells;   // [E] the agents' cells BEFORE the last step (8 x uint16), for the incremental observation update
@@ -558,6 +563,17 @@ k_step(const EnvDev d, const int32_t* __restrict__ actions, int32_t* __restrict_
     *reinterpret_cast<unsigned long long*>(d.step_flags + 2) = d.host_seq;
   }
   step_tile(d, actions, obs_xy, reward, done, smem_raw);
+  if (d.host_seq_out != nullptr) {  // uniform over the grid
+    __threadfence_system();         // this thread's result stores (host memory) are visible system-wide ...
+    __syncthreads();                // ... for every thread of the CTA, before the CTA checks in
+    if (threadIdx.x == 0 && atomicAdd(d.cta_counter, 1u) == gridDim.x - 1) {  // the last CTA: everything has landed
+      *d.cta_counter = 0u;
+      __threadfence();
+      d.host_flag_out[d.host_seq & 1ull] = *reinterpret_cast<volatile int32_t*>(d.step_flags + (d.host_seq & 1ull));
+      __threadfence_system();
+      *d.host_seq_out = d.host_seq;
+    }
+  }
 }
 
 // --------------------------------------------------------------------------------------------

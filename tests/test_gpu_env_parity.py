@@ -583,3 +583,67 @@ def test_corrupted_bucket_chain_cannot_hang_the_kernel():
     torch.cuda.synchronize()
     assert g.errors() & ~0x1F == 0
     g.close()
+
+
+@pytest.mark.parametrize("zc_out_kb,layout", [("256", "packed"), ("0", "packed"), ("0", "separate"), ("256", "separate"),
+                                              ("0", "pageable"), ("256", "mixed")])
+def test_host_step_result_paths_agree(monkeypatch, zc_out_kb, layout):
+    """rt_env_step_host returns obs_xy / reward / done three ways — stored by k_step itself into mapped host memory
+    (small batches), ONE copy-engine request when the caller's buffers are one pinned block laid out xy | reward |
+    done, three requests otherwise — and through pinned staging for pageable buffers.  All equal to the oracle,
+    a bad action is reported (and voids exactly its env) on every path."""
+    import ctypes as C
+
+    import torch
+    from oracle import oracle as O
+    from rad_team_b200 import _lib
+    from rad_team_b200.envs import BatchedRadSearchEnv
+
+    monkeypatch.setenv("RT_B200_ZC_OUT_KB", zc_out_kb)
+    E, A = 300, 3
+    kw = dict(O.DEFAULTS); kw.update(n_envs=E, n_agents=A, grid=32, max_steps=40, poly_min=1, poly_max=4, seed=77)
+    g, o = BatchedRadSearchEnv(**kw), O.OracleEnv(**kw)
+    L, st, n = _lib.lib(), torch.cuda.current_stream().cuda_stream, E * A
+    if layout == "packed":
+        block = torch.zeros(n * 13, dtype=torch.uint8).pin_memory()
+        xy = block[:n * 8].view(torch.int32).view(E, A, 2)
+        rew = block[n * 8:n * 12].view(torch.int32).view(E, A)
+        done = block[n * 12:].view(E, A)
+    elif layout == "separate":
+        xy = torch.zeros((E, A, 2), dtype=torch.int32).pin_memory()
+        rew = torch.zeros((E, A), dtype=torch.int32).pin_memory()
+        done = torch.zeros((E, A), dtype=torch.uint8).pin_memory()
+    elif layout == "pageable":
+        xy = torch.zeros((E, A, 2), dtype=torch.int32)
+        rew = torch.zeros((E, A), dtype=torch.int32)
+        done = torch.zeros((E, A), dtype=torch.uint8)
+    else:  # pinned positions, pageable reward, pinned done
+        xy = torch.zeros((E, A, 2), dtype=torch.int32).pin_memory()
+        rew = torch.zeros((E, A), dtype=torch.int32)
+        done = torch.zeros((E, A), dtype=torch.uint8).pin_memory()
+    h_act = torch.zeros((E, A), dtype=torch.int32).pin_memory()
+    g.reset()
+    o.reset()
+    rng = np.random.default_rng(77)
+    for t in range(25):
+        a_np = rng.integers(1, 5, size=(E, A)).astype(np.int32)
+        bad = t == 11
+        if bad:
+            a_np[17, 1] = 0
+        h_act.copy_(torch.from_numpy(a_np))
+        rc = L.rt_env_step_host(g._h, h_act.data_ptr(), xy.data_ptr(), rew.data_ptr(), done.data_ptr(),
+                                g.obs_maps.data_ptr(), st)
+        assert rc == (_lib.RT_ERR_BAD_ACTION if bad else _lib.RT_OK), (t, rc)
+        if bad:  # the oracle steps every env but 17, whose step the reference would have refused before any change
+            keep = o.export("AGENT_XY")[17].copy()
+            a_fix = a_np.copy(); a_fix[17, 1] = 1
+            xy_o, m_o, rew_o, done_o = o.step(a_fix)
+            sel = np.ones(E, bool); sel[17] = False
+            assert np.array_equal(xy.numpy()[sel], xy_o[sel]) and np.array_equal(rew.numpy()[sel], rew_o[sel])
+            assert np.array_equal(xy.numpy()[17], keep) and (rew.numpy()[17] == 0).all() and (done.numpy()[17] == 0).all()
+            break  # env 17 now differs from the oracle's: the comparison ends here
+        xy_o, m_o, rew_o, done_o = o.step(a_np)
+        assert np.array_equal(xy.numpy(), xy_o) and np.array_equal(rew.numpy(), rew_o), t
+        assert np.array_equal(done.numpy(), done_o), t
+        assert np.array_equal(g.obs_maps.cpu().numpy(), m_o), t
+    assert g.errors() == _lib.FLAG_BAD_ACTION
