@@ -591,8 +591,8 @@ def run_ours(args, rank, world, local_rank):
         E, base = w["envs"], rank * w["envs"]
     K, W = args.steps, max(args.warmup, 3)
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler = ClockSampler(local_rank, period=args.clock_period if args.clock_period > 0 else 3600.0)
+    sampler.start()  # (a period of 0 leaves one sample at the start: an A/B knob for the sampler's own cost)
     use_graph = args.graph == "on" or (args.graph == "auto" and wname == "c2")
     m = measure(cx, w, E, base, K, W, full=True, e2e_steps=args.e2e_steps, graph=use_graph)
     clocks = sampler.stop()
@@ -833,6 +833,7 @@ def main():
     ap.add_argument("--no-ref-python", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-k4b", action="store_true")
+    ap.add_argument("--clock-period", type=float, default=0.1, help="seconds between NVML clock samples")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

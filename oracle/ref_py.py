@@ -37,14 +37,18 @@ FILES = ["src/envs/__init__.py", "src/envs/simple_gridworld.py", "src/math_utils
          "src/math_utils/normalize.py", "src/math_utils/estimator.py"]
 
 
+def _bc_path(rel: str) -> Path:
+    """Byte-code file of one reference module.  Not named *.pyc: snapshot tools drop those as caches."""
+    return BYTECODE / (rel[:-3].replace("/", "__") + ".bytecode")
+
+
 def compile_reference(force: bool = False) -> bool:
-    """Byte-compile the reference's hot-path modules into oracle/_ref/refpy/ (sourceless .pyc files).
+    """Byte-compile the reference's hot-path modules into oracle/_ref/refpy/ (sourceless byte-code files).
     Returns False when the reference is not mounted (the GPU box): the prebuilt files are used as they are."""
     if not REF.exists():
         return False
     for rel in FILES:
-        src = REF / rel
-        dst = (BYTECODE / rel).with_suffix(".pyc")
+        src, dst = REF / rel, _bc_path(rel)
         if force or not dst.exists() or dst.stat().st_mtime < src.stat().st_mtime:
             dst.parent.mkdir(parents=True, exist_ok=True)
             py_compile.compile(str(src), cfile=str(dst), doraise=True, optimize=0)
@@ -52,7 +56,36 @@ def compile_reference(force: bool = False) -> bool:
 
 
 def available() -> bool:
-    return REF.exists() or all((BYTECODE / rel).with_suffix(".pyc").exists() for rel in FILES)
+    return REF.exists() or all(_bc_path(rel).exists() for rel in FILES)
+
+
+def _import_bytecode() -> None:
+    """Load the five compiled modules under their reference names (src.envs, src.envs.simple_gridworld,
+    src.math_utils.*) with sourceless loaders; `src` and `src.math_utils` are namespace packages in the reference."""
+    import importlib.machinery
+    import importlib.util
+
+    for ns in ("src", "src.math_utils"):
+        if ns not in sys.modules:
+            m = types.ModuleType(ns)
+            m.__path__ = []
+            sys.modules[ns] = m
+    for rel in FILES:
+        name = rel[:-3].replace("/", ".")
+        is_pkg = name.endswith(".__init__")
+        if is_pkg:
+            name = name[:-len(".__init__")]
+        if name in sys.modules and getattr(sys.modules[name], "__rt_bytecode__", False):
+            continue
+        loader = importlib.machinery.SourcelessFileLoader(name, str(_bc_path(rel)))
+        spec = importlib.util.spec_from_loader(name, loader, is_package=is_pkg)
+        mod = importlib.util.module_from_spec(spec)
+        mod.__rt_bytecode__ = True
+        sys.modules[name] = mod
+        loader.exec_module(mod)
+        parent, _, leaf = name.rpartition(".")
+        if parent:
+            setattr(sys.modules[parent], leaf, mod)
 
 
 def _install_shims() -> None:
@@ -98,9 +131,12 @@ def load_reference():
     if not available():
         raise FileNotFoundError("reference neither mounted at /root/reference nor byte-compiled under oracle/_ref/refpy")
     _install_shims()
-    root, origin = (REF, "source") if REF.exists() else (BYTECODE, "bytecode")
-    if str(root) not in sys.path:
-        sys.path.insert(0, str(root))
+    origin = "source" if REF.exists() else "bytecode"
+    if origin == "source":
+        if str(REF) not in sys.path:
+            sys.path.insert(0, str(REF))
+    else:
+        _import_bytecode()
     from src.envs.simple_gridworld import SimpleGrid
     from src.math_utils.estimator import IntensityResamplingEstimator
     from src.math_utils.normalize import BensLogNormalizer, Normalizer

@@ -111,3 +111,74 @@ def test_segment_inside_or_leaving_a_rectangle():
     assert O.rect_blocks([[1.5, 1.5, 6.5, 3.5]], rect)[0]       # leaves through one side
     assert O.rect_blocks([[0.5, 2.5, 5.5, 2.5]], rect)[0]       # straight through
     assert not O.rect_blocks([[0.5, 0.5, 5.5, 0.5]], rect)[0]   # passes below
+
+
+@pytest.mark.gpu
+def test_device_line_of_sight_and_refused_moves_match_the_integer_predicate():
+    """The DEVICE against the integer separating-axis predicate (no oracle in between): fixed scenarios on a 12 x 12
+    grid — every source cell x a spread of 1..5 rectangles — with 8 agents per env on assorted cells.  After every
+    step LAST_LOS must equal the number of rectangles the integer predicate counts on agent -> source, and a move
+    must have been refused exactly when the predicate says the centre-to-centre step crosses a rectangle."""
+    import torch
+    from rad_team_b200.envs import BatchedRadSearchEnv
+
+    G, A = 12, 8
+    rng = np.random.default_rng(2026)
+    n_src = G * G
+    E = n_src * 3                                   # every source cell, three rectangle sets each
+    src = np.stack([np.arange(E) % n_src % G, np.arange(E) % n_src // G], 1).astype(np.int32)
+    n_poly = rng.integers(1, 6, E).astype(np.int32)
+    rects = np.zeros((E, 5, 4), np.int64)           # x0, y0, x1, y1 (cell units)
+    edges = np.zeros((E, 20, 4), np.float32)
+    for e in range(E):
+        for p in range(n_poly[e]):
+            while True:
+                w, h = rng.integers(1, 6, 2)
+                x0, y0 = rng.integers(0, G - w + 1), rng.integers(0, G - h + 1)
+                if not (x0 <= src[e, 0] < x0 + w and y0 <= src[e, 1] < y0 + h):
+                    break
+            rects[e, p] = (x0, y0, x0 + w, y0 + h)
+            X0, Y0, X1, Y1 = map(float, rects[e, p])
+            edges[e, 4 * p:4 * p + 4] = [(X0, Y0, X1, Y0), (X1, Y0, X1, Y1), (X1, Y1, X0, Y1), (X0, Y1, X0, Y0)]
+    start = np.zeros((E, A, 2), np.int32)
+    for e in range(E):                              # starts outside every rectangle of the env
+        k = 0
+        while k < A:
+            c = rng.integers(0, G, 2)
+            if not any(r[0] <= c[0] < r[2] and r[1] <= c[1] < r[3] for r in rects[e, :n_poly[e]]):
+                start[e, k] = c
+                k += 1
+    env = BatchedRadSearchEnv(n_envs=E, n_agents=A, grid=G, max_steps=40, fixed_scenario=1, poly_min=0, poly_max=5,
+                              transmission=0.5, seed=3)
+    env.set_scenario(src_xy=src, src_int=np.full(E, 1e6), bkg=np.full(E, 20.0), start_xy=start, n_poly=n_poly,
+                     edges=edges)
+    env.reset()
+
+    def crossed(p, q):                              # [E, A] rectangles counted on p -> q, integer arithmetic
+        px, py, qx, qy = (2 * v.astype(np.int64) + 1 for v in (p[..., 0], p[..., 1], q[..., 0], q[..., 1]))
+        n = np.zeros(px.shape, np.int64)
+        for k in range(5):
+            r = 2 * rects[:, k][:, None, :]         # doubled, broadcast over agents
+            hit = sat_blocked(px, py, qx, qy, r[..., 0], r[..., 1], r[..., 2], r[..., 3])
+            n += hit & (k < n_poly)[:, None] & ((px != qx) | (py != qy))
+        return n
+
+    pos = start.copy()
+    d = {1: (0, 1), 2: (1, 0), 3: (-1, 0), 4: (0, -1)}
+    refused = moved = 0
+    for t in range(30):
+        act = rng.integers(1, 5, (E, A)).astype(np.int32)
+        xy, _, _, _, _ = env.step(torch.as_tensor(act, device=env.device))
+        step = np.array([d[a] for a in act.reshape(-1)], np.int32).reshape(E, A, 2)
+        cand = np.clip(pos + step, 0, G - 1)
+        block = crossed(pos, cand) > 0
+        want = np.where(block[..., None], pos, cand)
+        got = xy.cpu().numpy()
+        assert np.array_equal(got, want), f"step {t}: positions differ from the integer predicate's"
+        refused += int((block & (cand != pos).any(-1)).sum())
+        moved += int((~block & (cand != pos).any(-1)).sum())
+        pos = want
+        srcb = np.broadcast_to(src[:, None, :], pos.shape)
+        los = env.buffer("LAST_LOS").cpu().numpy()
+        assert np.array_equal(los, crossed(pos, srcb).astype(np.uint8)), f"step {t}: LAST_LOS"
+    assert refused > 1000 and moved > 10000 and env.errors() == 0
