@@ -191,13 +191,24 @@ int rt_env_step(rt_env* env, const int32_t* actions_dev, int32_t* obs_xy_dev, fl
 
 /* The same two calls with HOST buffers for everything the reference returns
  * to Python (obs, reward, done); the maps stay on the device (they are the
- * CNN's input tensor).  Pinned caller buffers are used directly (the step
- * kernel reads pinned actions in place over PCIe), pageable ones go through
- * pinned staging owned by the handle; the results travel back on an internal
- * stream while the rasteriser runs, and the call returns as soon as they have
- * landed: the rasterisation of obs_maps_dev may still be in flight on `stream`
- * (it is ordered before anything enqueued there later — the consumer network,
- * the next step — so the host's work between two steps hides under it).
+ * CNN's input tensor).  Pinned caller buffers are used directly, pageable ones
+ * go through pinned staging owned by the handle.  The step kernel reads pinned
+ * actions in place over PCIe.  The results return
+ *   - results of at most 256 KB (small batches): stored by the step kernel
+ *     itself into (mapped) host memory, its last CTA publishing a sequence
+ *     word — no copy-engine request at all;
+ *   - larger results: by the copy engine on an internal stream while the
+ *     rasteriser runs — ONE request when obs_xy_host, reward_host and
+ *     done_host are one pinned block laid out obs_xy | reward | done
+ *     (reward_host == obs_xy_host + 8 E A bytes, done_host == + 12 E A bytes),
+ *     three otherwise — followed by the sequence word;
+ * and the call returns as soon as that word has landed (it is polled in
+ * pinned memory, no driver call on the wait): the rasterisation of
+ * obs_maps_dev may still be in flight on `stream` (it is ordered before
+ * anything enqueued there later — the consumer network, the next step — so the
+ * host's work between two steps hides under it).  rt_env_reset_host likewise
+ * returns when the start positions have landed (with a mask: when `stream` has
+ * drained).
  * rt_env_step_host returns RT_ERR_BAD_ACTION when an action was
  * outside 1..4: the steps of exactly those envs were voided (no state change,
  * as in the reference, which raises before touching state); every other env
@@ -377,7 +388,9 @@ int rt_estimator_create(int64_t n, int32_t n_keys, int32_t capacity, rt_estimato
 int rt_estimator_destroy(rt_estimator* est);
 int rt_estimator_reset(rt_estimator* est, void* stream);
 /* .update(key, value) (estimator.py:31-48) once per estimator; writes the new
- * median estimate of that key to est_dev[i] (may be NULL). */
+ * median estimate of that key to est_dev[i] (may be NULL).  err_dev[i] =
+ * RT_ERR_BAD_ARG for a key outside [0, n_keys), RT_ERR_NOMEM when the
+ * estimator's `capacity` readings are used up (est_dev[i] is then NaN). */
 int rt_estimator_update(rt_estimator* est, const int32_t* key_dev, const double* value_dev,
                         double* est_dev, int32_t* err_dev, void* stream);
 /* .get_estimate(key) (estimator.py:61-70); RT_ERR_KEY in err_dev for a key

@@ -8,7 +8,7 @@ object is a parity surface for the reference's class, not a hot path.)"""
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Tuple
+from typing import Dict, List, Optional, Tuple
 
 from .. import _lib
 from .standardize import _view
@@ -85,10 +85,21 @@ class _ReadingsView(dict):
 class IntensityResamplingEstimator:
     """Scalar facade with the reference's method names (estimator.py:25-95)."""
 
-    def __init__(self, n_keys: int = 4096, capacity: int = 4096) -> None:
+    def __init__(self, readings: Optional[Dict[Tuple[int, int], List[float]]] = None, _min: float = 0.0,
+                 _max: float = 0.0, n_keys: int = 4096, capacity: int = 4096) -> None:
+        """`readings`, `_min`, `_max`: the reference dataclass's init fields (estimator.py:17-23; there is no
+        __post_init__, so a passed table seeds the estimator and the passed extrema stand).  `n_keys` / `capacity` size
+        the device pools (the reference's dict and lists are unbounded; exhaustion raises MemoryError naming the limit)."""
         self._b = BatchedEstimator(1, n_keys, capacity)
         self._slot: Dict[Tuple[int, int], int] = {}
         self._n_readings = 0
+        if readings:
+            for key, values in readings.items():
+                for v in values:
+                    self.update(key, v)
+        if readings or _min != 0.0 or _max != 0.0:  # seeding does not move the extrema in the reference
+            self._b.maxmin[0, 0] = float(_max)
+            self._b.maxmin[0, 1] = float(_min)
 
     # reference attributes
     @property

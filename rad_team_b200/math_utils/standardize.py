@@ -80,7 +80,10 @@ def _view(torch, ptr, shape, typestr, device):
 class WelfordsOnlineStandardization:
     """Scalar facade with the reference's attribute and method names (standardize.py:17-107)."""
 
-    def __init__(self) -> None:
+    def __init__(self, mean: float = 0.0, square_dist_mean: float = 0.0, sample_variance: float = 0.0,
+                 std: float = 1.0, count: int = 0) -> None:
+        # The reference is a dataclass with these init fields (standardize.py:17-26) whose __post_init__ calls
+        # reset() (:33-44): whatever is passed is overwritten by the defaults.  Same here: accepted, not used.
         self._b = BatchedWelford(1)
 
     def _s(self):

@@ -371,3 +371,22 @@ def test_batched_env_renders_an_rgb_frame_from_the_device_maps():
     if not any((src == a).all() for a in xy):
         assert tuple(frame[(15 - src[1]) * scale + scale // 2, src[0] * scale + scale // 2]) == (255, 0, 0)
     assert (frame[0, :, :] == 0).all() and (frame[:, 0, :] == 0).all()  # grid lines
+
+
+@pytest.mark.gpu
+def test_reference_dataclass_constructor_fields_are_honoured_like_the_reference_does():
+    from rad_team_b200.math_utils.estimator import IntensityResamplingEstimator
+    from rad_team_b200.math_utils.standardize import WelfordsOnlineStandardization
+
+    w = WelfordsOnlineStandardization(mean=5.0, std=3.0, count=7)   # the reference's __post_init__ resets them
+    assert (w.mean, w.std, w.count) == (0.0, 1.0, 0)
+    e = IntensityResamplingEstimator(readings={(1, 2): [1000, 2000, 500], (0, 0): [7]}, _max=9.0, _min=-1.0)
+    assert e.get_buffer((1, 2)) == [1000, 2000, 500] and e.get_estimate((1, 2)) == 1000
+    assert e.get_estimate((0, 0)) == 7 and (e.get_max(), e.get_min()) == (9.0, -1.0)
+    e.update((0, 0), 9)
+    assert e.get_estimate((0, 0)) == 8 and e.get_min() == -1.0 and e.get_max() == 9.0  # 8 < _max, 8 > _min: unchanged
+    small = IntensityResamplingEstimator(capacity=3)
+    for v in (1, 2, 3):
+        small.update((0, 0), v)
+    with pytest.raises(MemoryError, match="capacity=3"):
+        small.update((0, 0), 4)
