@@ -123,8 +123,10 @@ typedef enum rt_buf {
                             and the dense VISIT / INTENSITY views are brought up to date by each
                             rt_env_buffer(VISIT or INTENSITY) call (which synchronises the device);
                             with the dense rasterisers they are live */
-  RT_BUF_CELLREC = 12,   /* uint16 [E][G*G][4] per-cell record of the step kernel: unused, first bucket
-                            of the cell in LOG + 1 (0 = none), record index in VREC + 1
+  RT_BUF_CELLREC = 12,   /* uint16 [E][G*G][4] per-cell record of the step kernel: episode tag (low 16
+                            bits of EPISODE when the record was written; a record whose tag differs from
+                            the env's current episode is EMPTY — resets do not clear this array), first
+                            bucket of the cell in LOG + 1 (0 = none), record index in VREC + 1
                             (0 = not visited this episode), unused                          */
   RT_BUF_LOG = 13,       /* uint32 [T*A][E][8] reading buckets, time-major: 7 Poisson counts of ONE cell in
                             ascending order (the first min(7, rest) are valid) + a link word: low 16 bits =

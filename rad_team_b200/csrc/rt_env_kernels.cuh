@@ -38,9 +38,11 @@ struct EnvDev {
   uint16_t* visit;  // [E][cells]  dense visit counts: live only when live_dense, else materialised on request
   float* inten;     // [E][cells]  dense intensity map: likewise
   uint16_t* cellrec;  // [E][cells][4]  k_step's random-access state of a cell, ONE 8-byte record per cell so that a
-                      //   visit reads one DRAM sector (and a revisit writes none): [0] unused (the visit count
-                      //   travels with the cell's first bucket), [1] first bucket of the cell + 1 (0 = none),
-                      //   [2] record index in vrec + 1 (0 = not visited), [3] unused
+                      //   visit reads one DRAM sector (and a revisit writes none): [0] EPISODE TAG (low 16 bits of the
+                      //   env's episode number when the record was written: a record of an older episode counts as
+                      //   empty, so a reset clears nothing here except once every 65,536 episodes), [1] first bucket
+                      //   of the cell + 1 (0 = none; the visit count travels with that bucket), [2] record index in
+                      //   vrec + 1 (0 = not visited), [3] unused
   uint2* vrec;      // [E][rec_stride]  compact list of the VISITED cells, what the sparse rasteriser reads:
                     //   [0] = {n_visited, 0}; [1..2] = the agents' cells, 8 x uint16 (0xFFFF = none);
                     //   [2 + k] = {cell | visits << 16, fp32 bits of the intensity value}, k = 1..n_visited
@@ -177,14 +179,15 @@ __host__ __device__ inline size_t step_smem_bytes(int epb, int A) {
 // its bucket, cascades the evicted maximum down the chain, and picks the median — elements (n-1)/2 and n/2 of
 // the NEW sequence of n readings — on the way.  A chain that needs one more bucket takes slot `idx` = tick * A +
 // agent of the time-major pool, so no allocator state exists and a reset has nothing to clear.
-// `cur` = first bucket (+1, 0 = none); returns the median and, in n_out, the new number of readings.
-__device__ __forceinline__ double bucket_insert_median(uint4* __restrict__ pool, size_t E, uint16_t* head_cell,
-                                                       int idx, uint32_t cnt, int cur, int& n_out) {
-  if (cur == 0) {  // first reading of this cell
+// `cur` = first bucket (+1, 0 = none); `cell_rec` = the cell's 8-byte record, `tag` = the episode tag it gets with its
+// first bucket; returns the median and, in n_out, the new number of readings.
+__device__ __forceinline__ double bucket_insert_median(uint4* __restrict__ pool, size_t E, uint16_t* cell_rec,
+                                                       uint32_t tag, int idx, uint32_t cnt, int cur, int& n_out) {
+  if (cur == 0) {  // first reading of this cell in this episode
     uint4* np = pool + (size_t)idx * E * 2;
     np[0] = make_uint4(cnt, 0u, 0u, 0u);
     np[1] = make_uint4(0u, 0u, 0u, 1u << 16);
-    *head_cell = (uint16_t)(idx + 1);
+    *reinterpret_cast<uint32_t*>(cell_rec) = tag | ((uint32_t)(idx + 1) << 16);  // episode tag + first bucket
     n_out = 1;
     return (double)cnt;
   }
@@ -265,6 +268,7 @@ __device__ __forceinline__ double bucket_insert_median(uint4* __restrict__ pool,
 __device__ __forceinline__ void stats_chain(const EnvDev& d, const StepSmem& s, int e, int le, int tick,
                                             WelfordState& w, double emx, double emn, int nv) {
   const int A = d.A;
+  const uint32_t etag = (uint32_t)d.episode[e] & 0xffffu;
   uint16_t* crec = d.cellrec + (size_t)e * d.cells * 4;
   uint16_t* visit = d.visit + (size_t)e * d.cells;
   uint2* rec = d.vrec + (size_t)e * d.rec_stride;
@@ -280,10 +284,11 @@ __device__ __forceinline__ void stats_chain(const EnvDev& d, const StepSmem& s, 
       sl = s.slot[i];
     } else {
       const uint2 cr = *reinterpret_cast<const uint2*>(crec + 4 * cell);
-      est = bucket_insert_median(d.log + 2 * (size_t)e, (size_t)d.E, crec + 4 * cell + 1, tick * A + aa,
-                                 (uint32_t)s.count[i], (int)(cr.x >> 16), n);
+      const bool fresh = (cr.x & 0xffffu) == etag;  // written in THIS episode (an earlier agent of this very step)
+      est = bucket_insert_median(d.log + 2 * (size_t)e, (size_t)d.E, crec + 4 * cell, etag, tick * A + aa,
+                                 (uint32_t)s.count[i], fresh ? (int)(cr.x >> 16) : 0, n);
       if (d.live_dense) visit[cell] = (uint16_t)n;
-      sl = (int)(cr.y & 0xffffu);
+      sl = fresh ? (int)(cr.y & 0xffffu) : 0;
     }
     if (sl == 0) {  // first visit of this cell in the episode: open a record
       sl = ++nv;
@@ -464,9 +469,11 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
     s.cell[t] = cell;
     if (live) {  // cell state for the estimator: the loads fly while line of sight and sampler compute
       const size_t mcell = (size_t)e * d.cells + cell;
-      const uint2 cr = reinterpret_cast<const uint2*>(d.cellrec)[mcell];  // first bucket << 16, slot
-      ph = cr.x >> 16;
-      psl = cr.y & 0xffffu;
+      const uint2 cr = reinterpret_cast<const uint2*>(d.cellrec)[mcell];  // episode tag | first bucket << 16, slot
+      if ((cr.x & 0xffffu) == ((uint32_t)episode & 0xffffu)) {  // else: a record of an older episode = empty
+        ph = cr.x >> 16;
+        psl = cr.y & 0xffffu;
+      }
       // The owner will write this cell's 8-byte visited-cell record at the end.  A partial write into a sector
       // that is NOT in the L2 is dear for whoever reads it next (the rasteriser): fetch the sector now, the write
       // then lands in a complete line (-1.6 % on the step, profiles/r03m).
@@ -510,8 +517,8 @@ __device__ __forceinline__ void step_tile(const EnvDev& d, const int32_t* __rest
     double est = 0.0;
     if (!clash) {
       uint16_t* cr16 = d.cellrec + ((size_t)e * d.cells + cell) * 4;
-      est = bucket_insert_median(d.log + 2 * (size_t)e, (size_t)d.E, cr16 + 1, tick * A + a, (uint32_t)cnt, (int)ph,
-                                 n);
+      est = bucket_insert_median(d.log + 2 * (size_t)e, (size_t)d.E, cr16, (uint32_t)episode & 0xffffu, tick * A + a,
+                                 (uint32_t)cnt, (int)ph, n);
       if (d.live_dense) d.visit[(size_t)e * d.cells + cell] = (uint16_t)n;
     }
     s.count[t] = (int)cnt;
@@ -689,23 +696,29 @@ k_reset_state(const EnvDev d, const uint8_t* __restrict__ mask, int32_t* __restr
   reinterpret_cast<double2*>(d.est_mm)[e] = make_double2(0.0, 0.0);  // estimator.py:25-29
 }
 
-// cell records (8 B) + dense visit (2 B) + dense intensity (4 B) per cell; 16-byte stores, one CTA per env.
+// dense visit (2 B) + dense intensity (4 B) per cell when a dense rasteriser keeps them, and the cell records (8 B per
+// cell) only when their episode tag wraps; 16-byte stores, one CTA per env (which exits at once when it has nothing to do).
 __global__ void __launch_bounds__(256)
 k_zero_maps(const EnvDev d, const uint8_t* __restrict__ mask) {
   const int e = blockIdx.x;
   if (mask != nullptr && mask[e] == 0) return;
+  // cell records carry an episode tag: a reset leaves them alone, except when the 16-bit tag wraps (the episode
+  // number k_reset_state has just written is a multiple of 65,536 — also the very first episode, over a zeroed slab)
+  if (!d.live_dense && (d.episode[e] & 0xffff) != 0) return;
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
   const size_t b16 = (size_t)d.cells * 2, b32 = (size_t)d.cells * 4, b64 = (size_t)d.cells * 8;
   unsigned char* v = reinterpret_cast<unsigned char*>(d.visit) + (size_t)e * b16;
   unsigned char* c = reinterpret_cast<unsigned char*>(d.cellrec) + (size_t)e * b64;
   unsigned char* f = reinterpret_cast<unsigned char*>(d.inten) + (size_t)e * b32;
-  if ((d.cells & 1) == 0) {  // an env's cell records start 16-byte aligned only when cells is even
-    for (size_t i = threadIdx.x * 16; i < b64; i += blockDim.x * 16) *reinterpret_cast<uint4*>(c + i) = z;
-  } else {
-    for (size_t i = threadIdx.x * 8; i < b64; i += blockDim.x * 8) *reinterpret_cast<uint2*>(c + i) = make_uint2(0u, 0u);
+  if ((d.episode[e] & 0xffff) == 0) {
+    if ((d.cells & 1) == 0) {  // an env's cell records start 16-byte aligned only when cells is even
+      for (size_t i = threadIdx.x * 16; i < b64; i += blockDim.x * 16) *reinterpret_cast<uint4*>(c + i) = z;
+    } else {
+      for (size_t i = threadIdx.x * 8; i < b64; i += blockDim.x * 8) *reinterpret_cast<uint2*>(c + i) = make_uint2(0u, 0u);
+    }
   }
   // the dense visit / intensity maps are only kept when a dense rasteriser reads them; otherwise they are
-  // materialised on request (rt_env_buffer clears them first) and a reset has 8 of 14 KB per env to clear
+  // materialised on request (rt_env_buffer clears them first) and a reset clears nothing here
   if (!d.live_dense) return;
   if ((d.cells & 7) == 0) {
     for (size_t i = threadIdx.x * 16; i < b16; i += blockDim.x * 16) *reinterpret_cast<uint4*>(v + i) = z;
@@ -1142,7 +1155,8 @@ k_patch_incremental(const EnvDev d, float* __restrict__ out) {
     const uint32_t c = (curw[a >> 1] >> (16 * (a & 1))) & 0xffffu;
     if (c != 0xffffu) {
       o[c] = 1.0f;
-      const int sl = (int)d.cellrec[((size_t)e * d.cells + c) * 4 + 2];
+      const uint16_t* crc = d.cellrec + ((size_t)e * d.cells + c) * 4;
+      const int sl = crc[0] == (uint16_t)(d.episode[e] & 0xffff) ? (int)crc[2] : 0;  // older episode = not visited
       if (sl != 0) {  // visited this episode (always, after a step; not for a voided env still on its start cell)
         const uint2 r = rec[2 + sl];  // {cell | visits << 16, fp32 intensity}
         o[d.cells + c] = __uint_as_float(r.y);

@@ -647,3 +647,36 @@ def test_host_step_result_paths_agree(monkeypatch, zc_out_kb, layout):
         assert np.array_equal(done.numpy(), done_o), t
         assert np.array_equal(g.obs_maps.cpu().numpy(), m_o), t
     assert g.errors() == _lib.FLAG_BAD_ACTION
+
+
+def test_cell_records_survive_resets_by_episode_tag_including_the_16_bit_wrap():
+    """A reset does not clear the per-cell records: they carry the low 16 bits of the episode number and a record of
+    an older episode counts as empty; when the tag wraps (episode 65,536) the records ARE cleared.  Checked against a
+    host-side tally of the agents' paths — visit counts per cell and the number of distinct visited cells — across
+    episodes 65,533 ... 65,538, with and without the dense maps."""
+    import torch
+    from oracle import oracle as O
+    from rad_team_b200.envs import BatchedRadSearchEnv
+
+    kw = dict(O.DEFAULTS); kw.update(n_envs=24, n_agents=2, grid=8, max_steps=40, seed=99)
+    env = BatchedRadSearchEnv(**kw)
+    E, A, G, T = 24, 2, 8, 40
+    env.buffer("EPISODE").fill_(65532)          # the next reset opens episode 65,533
+    rng = np.random.default_rng(99)
+    for ep in range(65533, 65539):
+        xy, _ = env.reset()
+        assert int(env.buffer("EPISODE")[0].item()) == ep
+        tally = np.zeros((E, G * G), np.int64)
+        for t in range(T):
+            act = torch.as_tensor(rng.integers(1, 5, size=(E, A)).astype(np.int32), device=env.device)
+            xy, _, _, _, _ = env.step(act)
+            p = xy.cpu().numpy()
+            for a in range(A):
+                np.add.at(tally, (np.arange(E), p[:, a, 1] * G + p[:, a, 0]), 1)
+            if t in (0, 7, T - 1):
+                assert np.array_equal(env.buffer("VISIT").cpu().numpy().astype(np.int64), tally), (ep, t)
+                assert np.array_equal(env.buffer("VREC")[:, 0, 0].cpu().numpy(), (tally > 0).sum(1)), (ep, t)
+                lut = env.buffer("VISIT_LUT").cpu().numpy()
+                maps = env.obs_maps.cpu().numpy().reshape(E, 3, G * G)
+                assert np.array_equal(maps[:, 2], lut[tally]), (ep, t)     # the visit channel = table[tally]
+        assert env.errors() == 0
