@@ -249,6 +249,19 @@ int rt_env_set_rollout(rt_env* env, float* readings_dev);
  * next to its moments, to the once-per-rollout all-gather. */
 int rt_env_episode_stats(rt_env* env, double* stats_dev, void* stream);
 
+/* Checkpoint / deterministic replay for hosts that do not want to walk rt_buf:
+ * the handle's whole persistent state (every rt_buf array, RNG positions are
+ * functions of it) as ONE opaque blob.  rt_env_state_bytes gives its size;
+ * rt_env_get_state copies it to `dst` and rt_env_set_state restores it from
+ * `src` (host or device memory, cudaMemcpyDefault) in stream order; set_state
+ * checks that the blob came from a handle of the same shape (else
+ * RT_ERR_BAD_ARG) and SYNCHRONISES `stream` when `src` is pageable host memory.
+ * The reference env has no such call ("expose a
+ * state_dict-style export for deterministic replay"). */
+int rt_env_state_bytes(const rt_env* env, size_t* bytes);
+int rt_env_get_state(rt_env* env, void* dst, void* stream);
+int rt_env_set_state(rt_env* env, const void* src, void* stream);
+
 /* Raw device view of one state array (see rt_buf). */
 int rt_env_buffer(rt_env* env, int which, void** dev_ptr, size_t* bytes);
 /* OR of all envs' sticky flags -> *flags_host.  Synchronises `stream`. */

@@ -56,6 +56,9 @@ SYMBOLS = {
     "rt_env_inject_uniforms": (C.c_int, [_vp, _vp, _i32]),
     "rt_env_set_rollout": (C.c_int, [_vp, _vp]),
     "rt_env_episode_stats": (C.c_int, [_vp, _vp, _vp]),
+    "rt_env_state_bytes": (C.c_int, [_vp, C.POINTER(C.c_size_t)]),
+    "rt_env_get_state": (C.c_int, [_vp, _vp, _vp]),
+    "rt_env_set_state": (C.c_int, [_vp, _vp, _vp]),
     "rt_env_buffer": (C.c_int, [_vp, C.c_int, _pp, C.POINTER(C.c_size_t)]),
     "rt_env_errors": (C.c_int, [_vp, C.POINTER(_i32), _vp]),
     "rt_env_launch_count": (_i64, [_vp]),

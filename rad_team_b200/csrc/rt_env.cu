@@ -751,6 +751,59 @@ int rt_env_episode_stats(rt_env* h, double* stats_dev, void* stream) {
   return RT_OK;
 }
 
+namespace {
+struct StateHeader {  // 64 bytes in front of the slab image
+  uint64_t magic;
+  int32_t abi, E, A, G, T, reserved;
+  uint64_t slab_bytes;
+  unsigned char pad[24];
+};
+static_assert(sizeof(StateHeader) == 64, "state header is 64 bytes");
+constexpr uint64_t kStateMagic = 0x3142544152545352ull;  // "RSTRATB1"
+}  // namespace
+
+int rt_env_state_bytes(const rt_env* h, size_t* bytes) {
+  if (!h || !bytes) return RT_ERR_BAD_ARG;
+  *bytes = sizeof(StateHeader) + h->slab_bytes;
+  return RT_OK;
+}
+
+int rt_env_get_state(rt_env* h, void* dst, void* stream) {
+  if (!h || !dst) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  StateHeader hd = {};
+  hd.magic = kStateMagic;
+  hd.abi = RT_ABI_VERSION;
+  hd.E = h->dev.E; hd.A = h->dev.A; hd.G = h->dev.G; hd.T = h->dev.T;
+  hd.slab_bytes = h->slab_bytes;
+  // the header goes through a synchronous copy (it lives on this stack frame), the slab in stream order
+  RT_CUDA(cudaStreamSynchronize(st));
+  RT_CUDA(cudaMemcpy(dst, &hd, sizeof hd, cudaMemcpyDefault));
+  RT_CUDA(cudaMemcpyAsync(static_cast<unsigned char*>(dst) + sizeof hd, h->slab, h->slab_bytes, cudaMemcpyDefault, st));
+  return RT_OK;
+}
+
+int rt_env_set_state(rt_env* h, const void* src, void* stream) {
+  if (!h || !src) return RT_ERR_BAD_ARG;
+  RtDeviceGuard on_device(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  StateHeader hd;
+  RT_CUDA(cudaStreamSynchronize(st));
+  RT_CUDA(cudaMemcpy(&hd, src, sizeof hd, cudaMemcpyDefault));
+  if (hd.magic != kStateMagic || hd.abi != RT_ABI_VERSION || hd.E != h->dev.E || hd.A != h->dev.A ||
+      hd.G != h->dev.G || hd.T != h->dev.T || hd.slab_bytes != h->slab_bytes)
+    return RT_ERR_BAD_ARG;
+  RT_CUDA(cudaMemcpyAsync(h->slab, static_cast<const unsigned char*>(src) + sizeof hd, h->slab_bytes,
+                          cudaMemcpyDefault, st));
+  // the slab also holds the host path's scratch words (voided-step flags, sequence stamp, CTA check-in counter):
+  // they belong to the calls in flight, not to the env's state
+  RT_CUDA(cudaMemsetAsync(h->d_flag_or, 0, 32, st));
+  if (!is_pinned_or_device(src)) RT_CUDA(cudaStreamSynchronize(st));
+  h->last_maps = nullptr;  // no tensor holds this state's observation
+  return RT_OK;
+}
+
 int rt_env_buffer(rt_env* h, int which, void** dev_ptr, size_t* bytes) {
   if (!h || which < 0 || which >= RT_BUF__COUNT || !h->buf_ptr[which]) return RT_ERR_BAD_ARG;
   RtDeviceGuard on_device(h->device);

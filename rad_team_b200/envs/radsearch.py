@@ -190,6 +190,25 @@ class BatchedRadSearchEnv:
         for k, v in sd.items():
             self.buffer(k).copy_(v)
 
+    def get_state(self, out=None):
+        """The handle's whole persistent state as ONE opaque uint8 CUDA tensor (rt_env_get_state): checkpoint /
+        deterministic replay without walking the named buffers."""
+        t = self._torch
+        n = C.c_size_t()
+        _lib.check(self._L.rt_env_state_bytes(self._h, C.byref(n)))
+        out = t.empty(n.value, dtype=t.uint8, device=self.device) if out is None else out
+        _lib.require(out.dtype == t.uint8 and out.is_contiguous() and out.numel() == n.value, "state blob size / dtype")
+        with self._on_device():
+            _lib.check(self._L.rt_env_get_state(self._h, out.data_ptr(), self._stream()), "rt_env_get_state")
+        return out
+
+    def set_state(self, blob) -> None:
+        """Restore a blob from get_state() of an env of the same shape (ValueError otherwise)."""
+        t = self._torch
+        _lib.require(blob.dtype == t.uint8 and blob.is_contiguous(), "state blob must be a contiguous uint8 tensor")
+        with self._on_device():
+            _lib.check(self._L.rt_env_set_state(self._h, blob.data_ptr(), self._stream()), "rt_env_set_state")
+
     def set_scenario(self, src_xy=None, src_int=None, bkg=None, start_xy=None, n_poly=None, edges=None) -> None:
         E, A = self.E, self.A
 

@@ -680,3 +680,41 @@ def test_cell_records_survive_resets_by_episode_tag_including_the_16_bit_wrap():
                 maps = env.obs_maps.cpu().numpy().reshape(E, 3, G * G)
                 assert np.array_equal(maps[:, 2], lut[tally]), (ep, t)     # the visit channel = table[tally]
         assert env.errors() == 0
+
+
+def test_get_state_set_state_replays_bit_exactly():
+    """rt_env_get_state / rt_env_set_state: snapshot mid-episode, run on, restore, run the same actions again — every
+    output and the final state are identical; a blob of another shape is refused; works through host memory too."""
+    import torch
+    from oracle import oracle as O
+    from rad_team_b200.envs import BatchedRadSearchEnv
+
+    kw = dict(O.DEFAULTS); kw.update(n_envs=130, n_agents=3, grid=32, max_steps=60, poly_min=1, poly_max=5, seed=5)
+    env = BatchedRadSearchEnv(**kw)
+    rng = np.random.default_rng(5)
+    acts = torch.as_tensor(rng.integers(1, 5, size=(50, 130, 3)).astype(np.int32), device=env.device)
+    env.reset()
+    for t in range(20):
+        env.step(acts[t])
+    blob = env.get_state()
+    host_blob = blob.cpu()                          # pageable host memory
+
+    def run():
+        outs = []
+        for t in range(20, 50):
+            xy, rw, dn, _, _ = env.step(acts[t])
+            outs.append((xy.clone(), rw.clone(), dn.clone(), env.buffer("LAST_COUNT").clone(), env.obs_maps.clone()))
+        return outs, env.get_state()
+
+    first, end1 = run()
+    env.set_state(blob)
+    second, end2 = run()
+    env.set_state(host_blob)
+    third, end3 = run()
+    for a, b, c in zip(first, second, third):
+        for x, y, z in zip(a, b, c):
+            assert torch.equal(x, y) and torch.equal(x, z)
+    assert torch.equal(end1, end2) and torch.equal(end1, end3)
+    other = BatchedRadSearchEnv(**dict(kw, n_envs=131))
+    with pytest.raises(ValueError):
+        other.set_state(blob[: other.get_state().numel()] if blob.numel() >= other.get_state().numel() else blob)
