@@ -10,6 +10,7 @@ from typing import Any, Dict, Optional, Tuple
 
 import numpy as np
 
+from .. import _lib
 from .radsearch import BatchedRadSearchEnv, RadSearchConfig
 
 try:  # the reference subclasses gymnasium.Env; do the same when gymnasium is installed
@@ -79,6 +80,10 @@ class SimpleGrid(_Base):
         action = Action(action)  # ValueError("0 is not a valid Action") like the reference (:138)
         xy, rew, done, trunc, _ = self._env.step(np.array([[int(action)]], dtype=np.int32))
         flags = self._env.errors()
+        if flags & _lib.FLAG_LOG_FULL:
+            # the reference env has no episode length limit; the device keeps a bounded per-env reading log
+            raise MemoryError(f"episode longer than max_steps={self._env.cfg.max_steps} steps without reset(): the device "
+                              "reading log is bounded (max_steps * agents <= 65534); the step was not executed")
         if flags:
             raise Exception(f"Something has gone wrong in the step function (device flags {flags:#x})")
         self.agent = xy[0, 0].astype(np.int32)

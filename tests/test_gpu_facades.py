@@ -390,3 +390,16 @@ def test_reference_dataclass_constructor_fields_are_honoured_like_the_reference_
         small.update((0, 0), v)
     with pytest.raises(MemoryError, match="capacity=3"):
         small.update((0, 0), 4)
+
+
+@pytest.mark.gpu
+def test_simplegrid_episode_cap_is_reported_as_a_named_limit():
+    from rad_team_b200.envs.simple_gridworld import SimpleGrid
+
+    env = SimpleGrid(np.array([5, 5], np.int32), np.array([0, 0], np.int32), size=10, max_steps=3)
+    env.reset()
+    for _ in range(3):
+        env.step(1)
+    with pytest.raises(MemoryError, match="max_steps=3"):
+        env.step(1)
+    env.reset()          # a reset opens a new log; the sticky flag of the old episode stays readable but the env works
