@@ -115,3 +115,42 @@ def test_extreme_configurations_vs_oracle(kw):
         assert np.array_equal(g.obs_maps.cpu().numpy(), m_o), t
     assert np.array_equal(g.buffer("VISIT_LUT").cpu().numpy(), o.export("VISIT_LUT"))
     assert g.errors() == o.errors() == 0
+
+
+def test_c4_shard_of_rank_7_of_8_sampled_oracle_parity():
+    """BASELINE configs[3] as rank 7 of 8 sees it: 131,072 envs whose GLOBAL ids start at 917,504.  Sampled blocks of
+    the shard are reproduced by 64-env oracles placed at the same global ids (RNG streams are functions of the global
+    env id, so this is also what a one-GPU run of all 1,048,576 envs computes for them)."""
+    import torch
+    from oracle import oracle as O
+    from rad_team_b200.distributed import shard_range
+    from rad_team_b200.envs import BatchedRadSearchEnv
+
+    base, count = shard_range(1_048_576, 7, 8)
+    assert (base, count) == (917_504, 131_072)
+    cfg = dict(n_envs=count, n_agents=3, grid=32, max_steps=120, poly_min=1, poly_max=5, seed=0, env_id_base=base)
+    env = BatchedRadSearchEnv(**cfg)
+    T = 24
+    gen = torch.Generator(device=env.device); gen.manual_seed(9)
+    acts = torch.randint(1, 5, (T, count, 3), dtype=torch.int32, device=env.device, generator=gen)
+    offs = [0, 70_001, count - 64]
+    orcs = []
+    for off in offs:
+        kw = dict(O.DEFAULTS); kw.update(cfg); kw.update(n_envs=64, env_id_base=base + off)
+        orcs.append(O.OracleEnv(**kw))
+    xy, _ = env.reset()
+    for off, o in zip(offs, orcs):
+        xy_o, m_o = o.reset()
+        assert np.array_equal(xy[off:off + 64].cpu().numpy(), xy_o)
+        assert np.array_equal(env.obs_maps[off:off + 64].cpu().numpy(), m_o)
+    for t in range(T):
+        xy, rew, done, _, _ = env.step(acts[t])
+        for off, o in zip(offs, orcs):
+            xy_o, m_o, rew_o, done_o = o.step(acts[t, off:off + 64].cpu().numpy())
+            assert np.array_equal(xy[off:off + 64].cpu().numpy(), xy_o), (t, off)
+            assert np.array_equal(rew[off:off + 64].cpu().numpy(), rew_o)
+            assert np.array_equal(env.buffer("LAST_COUNT")[off:off + 64].cpu().numpy(), o.export("LAST_COUNT"))
+            assert np.array_equal(env.buffer("LAST_LOS")[off:off + 64].cpu().numpy(), o.export("LAST_LOS"))
+            assert np.array_equal(env.obs_maps[off:off + 64].cpu().numpy(), m_o), (t, off)
+    visit = env.buffer("VISIT").to(torch.int32)
+    assert torch.all(visit.sum(1) == T * 3) and env.errors() == 0
