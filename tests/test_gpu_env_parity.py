@@ -718,3 +718,55 @@ def test_get_state_set_state_replays_bit_exactly():
     other = BatchedRadSearchEnv(**dict(kw, n_envs=131))
     with pytest.raises(ValueError):
         other.set_state(blob[: other.get_state().numel()] if blob.numel() >= other.get_state().numel() else blob)
+
+
+@pytest.mark.parametrize("E,A,raster", [(4096, 1, "auto"), (1024, 3, "auto"), (4096, 1, "sparse_lsu")])
+def test_whole_episode_cuda_graph_replay_matches_eager_launches(monkeypatch, E, A, raster):
+    """A captured CUDA graph of a whole episode (120 x (k_step + rasteriser) + reset), replayed back to back — no host
+    gaps, programmatic dependent launches overlapping every kernel with its neighbours — must leave exactly the state,
+    readings and observation of the same episode launched eagerly.  (Small batches use k_raster_small, which writes
+    its zeros BEFORE its dependency wait: this is the test that would catch a rasteriser running ahead of the
+    previous step's.)"""
+    import torch
+    from oracle import oracle as O
+    from rad_team_b200.envs import BatchedRadSearchEnv
+
+    monkeypatch.setenv("RT_B200_RASTER", raster)
+    kw = dict(O.DEFAULTS); kw.update(n_envs=E, n_agents=A, grid=32, max_steps=120, poly_min=0, poly_max=3, seed=61)
+    a, b = BatchedRadSearchEnv(**kw), BatchedRadSearchEnv(**kw)
+    T = 120
+    gen = torch.Generator(device=a.device); gen.manual_seed(3)
+    acts = torch.randint(1, 5, (T, E, A), dtype=torch.int32, device=a.device, generator=gen)
+    ra = torch.zeros((T, E, A), dtype=torch.float32, device=a.device)
+    rb = torch.zeros_like(ra)
+    a.set_rollout(ra); b.set_rollout(rb)
+    mid_a = torch.empty_like(a.obs_maps); mid_b = torch.empty_like(b.obs_maps)
+
+    def episode(env, mid):
+        env.reset()
+        for t in range(T):
+            env.step(acts[t])
+            if t == 59:
+                mid.copy_(env.obs_maps)   # a consumer reading the tensor between two steps
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        episode(b, mid_b)                 # warm-up outside the capture
+        side.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            episode(b, mid_b)
+        for _ in range(3):                # episodes 1, 2, 3 of env b (episode 0 was the warm-up... see below)
+            g.replay()
+        side.synchronize()
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(4):                    # env a: the same four episodes, eagerly
+        episode(a, mid_a)
+    torch.cuda.synchronize()
+    assert torch.equal(a.buffer("EPISODE"), b.buffer("EPISODE"))
+    assert torch.equal(mid_a, mid_b)
+    assert torch.equal(a.obs_maps, b.obs_maps) and torch.equal(ra, rb)
+    for k in ("VREC", "CELLREC", "WELFORD", "LOG", "AGENT_XY", "EST_MAXMIN"):
+        assert torch.equal(a.buffer(k), b.buffer(k)), k
+    assert a.errors() == b.errors() == 0
