@@ -79,3 +79,42 @@ def test_product_never_imports_the_oracle():
     assert len(files) > 8
     for f in files:
         assert not pat.search(f.read_text()), f
+
+
+def test_header_is_plain_c_and_the_integration_stub_compiles(tmp_path):
+    """include/rt_b200.h must be consumable by a C99 compiler (the drop-in boundary is a C ABI), and the C snippet of
+    INTEGRATION.md section 5 must compile against it."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc") or "/usr/bin/gcc"
+    src = tmp_path / "stub.c"
+    src.write_text(r'''
+#include "rt_b200.h"
+int run_rollout_close(int rank, int world, rt_env* env, const float* readings_dev, long long n, double* ep_dev,
+                      double* ep_sum_dev, void* stream) {
+  rt_comm* comm;
+  rt_moments *local, *global;
+  int rc = rt_comm_create_shm("/my_job_1234", rank, world, &comm);
+  if (rc != RT_OK) return rc;
+  rt_moments_create(&local);
+  rt_moments_create(&global);
+  rt_moments_update(local, readings_dev, n, stream);
+  rt_env_episode_stats(env, ep_dev, stream);
+  rc = rt_stats_allgather_merge(comm, local, global, ep_dev, ep_sum_dev, 0, stream);
+  rt_comm_disconnect(comm);
+  rt_comm_destroy(comm);
+  return rc;
+}
+int main(void) {
+  rt_env_cfg cfg = {0};
+  size_t bytes = 0;
+  cfg.n_envs = 4; cfg.n_agents = 1; cfg.grid = 8; cfg.max_steps = 10; cfg.lognorm_step = 2;
+  cfg.cell_pitch_cm = 100.0; cfg.min_dist_cm = 50.0;
+  (void)bytes;
+  return (int)sizeof(cfg) == 96 && RT_ABI_VERSION == 1 && RT_COMM_HANDLE_BYTES == 64 ? 0 : 1;
+}
+''')
+    out = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", str(HEADER.parent), "-c",
+                          str(src), "-o", str(tmp_path / "stub.o")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
