@@ -182,3 +182,25 @@ def test_device_line_of_sight_and_refused_moves_match_the_integer_predicate():
         los = env.buffer("LAST_LOS").cpu().numpy()
         assert np.array_equal(los, crossed(pos, srcb).astype(np.uint8)), f"step {t}: LAST_LOS"
     assert refused > 1000 and moved > 10000 and env.errors() == 0
+
+
+def test_unit_moves_cross_a_rectangle_iff_exactly_one_cell_is_inside():
+    """The collision rule (N4) on the generated scenarios: for a move between neighbouring cells the edge tests reduce
+    to "exactly one of the two cells lies inside the rectangle" — every rectangle and every unit move of a 12 x 12 grid."""
+    G = 12
+    moves = []
+    for y in range(G):
+        for x in range(G):
+            for dx, dy in ((1, 0), (-1, 0), (0, 1), (0, -1)):
+                if 0 <= x + dx < G and 0 <= y + dy < G:
+                    moves.append((x, y, x + dx, y + dy))
+    m = np.asarray(moves, np.int64)
+    segs = (m + 0.5).astype(np.float32)
+    for w in range(1, G + 1):
+        for h in range(1, G + 1):
+            for x0 in range(0, G - w + 1):
+                for y0 in range(0, G - h + 1):
+                    p_in = (m[:, 0] >= x0) & (m[:, 0] < x0 + w) & (m[:, 1] >= y0) & (m[:, 1] < y0 + h)
+                    q_in = (m[:, 2] >= x0) & (m[:, 2] < x0 + w) & (m[:, 3] >= y0) & (m[:, 3] < y0 + h)
+                    got = O.rect_blocks(segs, [x0, y0, x0 + w, y0 + h]).astype(bool)
+                    assert np.array_equal(got, p_in ^ q_in), (x0, y0, w, h)
