@@ -250,7 +250,7 @@ int launch_step(rt_env* h, const int32_t* actions, int32_t* obs_xy, float* obs_m
 int launch_reset(rt_env* h, const uint8_t* mask, int32_t* obs_xy, float* obs_maps, cudaStream_t st) {
   const EnvDev& d = h->dev;
   k_reset_state<<<(unsigned)((d.E + 127) / 128), 128, 0, st>>>(d, mask, obs_xy);
-  k_zero_maps<<<(unsigned)d.E, 256, 0, st>>>(d, mask);
+  k_zero_maps<<<(unsigned)std::min<long long>(d.E, (long long)h->n_sm * 8), 256, 0, st>>>(d, mask);
   h->launches += 2;
   RT_CUDA_LAUNCH_CHECK();
   if (obs_maps) return launch_raster(h, obs_maps, st);
@@ -579,7 +579,7 @@ int rt_env_reset_host(rt_env* h, const uint8_t* mask_host, int32_t* obs_xy_host,
     void* dst = direct ? (void*)obs_xy_host : (void*)(h->pinned + E * A * 4);
     RT_CUDA(cudaMemcpyAsync(dst, h->d_obs_xy, E * A * 8, cudaMemcpyDefault, h->aux));
   }
-  k_zero_maps<<<(unsigned)d.E, 256, 0, st>>>(d, mask_dev);
+  k_zero_maps<<<(unsigned)std::min<long long>(d.E, (long long)h->n_sm * 8), 256, 0, st>>>(d, mask_dev);
   h->launches += 1;
   RT_CUDA_LAUNCH_CHECK();
   if (obs_maps_dev) {
