@@ -344,7 +344,7 @@ int rt_moments_merge(rt_moments* m, const double* gathered_dev, int32_t n_ranks,
  *       wait, merge.  No library collective, no host round trip, CUDA-graph
  *       capturable.  Collective semantics: every rank must call it the same
  *       number of times; a peer that does not arrive within the timeout
- *       (RT_B200_COMM_TIMEOUT_MS, default 5000) sets a sticky error
+ *       (RT_B200_COMM_TIMEOUT_MS, default 30000) sets a sticky error
  *       (rt_comm_errors) instead of hanging the device.
  *   (2) rt_stats_pack -> the caller's all-gather of 6 doubles per rank (NCCL
  *       through torch.distributed, MPI, ...) -> rt_stats_merge_gathered. */

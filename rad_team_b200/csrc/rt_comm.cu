@@ -178,7 +178,7 @@ struct rt_comm {
   double* peer[RT_COMM_MAX_RANKS] = {};       // mapped peers (peer[rank] == mailbox)
   bool opened[RT_COMM_MAX_RANKS] = {};
   bool connected = false;
-  unsigned long long timeout_ns = 5000000000ull;
+  unsigned long long timeout_ns = 30000000000ull;  // 30 s: ranks may legitimately be seconds apart (logging, checkpoints)
   size_t mailbox_bytes = 0;
 };
 
