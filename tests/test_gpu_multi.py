@@ -63,3 +63,56 @@ def test_eight_gpus_sharded_run_matches_one_gpu_and_merges_bit_identically():
     if torch.cuda.device_count() < 8:
         pytest.skip("needs 8 GPUs (run under gpurun --gpus 8)")
     _run(8, same_gpu=False)
+
+
+TIMEOUT_WORKER = r"""
+import os, sys, time
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["RT_REPO"])
+from rad_team_b200.distributed import RolloutStatsExchange
+from rad_team_b200.math_utils import RunningMoments
+rank = int(os.environ["RANK"])
+torch.cuda.set_device(0)
+dist.init_process_group("gloo")
+ex = RolloutStatsExchange(backend="peer")
+loc, glob = RunningMoments(), RunningMoments()
+x = torch.arange(1000, dtype=torch.float32, device="cuda") + rank
+loc.update(x); ex.exchange(loc, glob, None); torch.cuda.synchronize()
+assert glob.state[0].item() == 2000 and ex.errors() == 0          # a normal exchange first
+dist.barrier()
+if rank == 0:                                                       # rank 1 never shows up for the second one
+    loc.update(x)
+    t0 = time.time()
+    ex.exchange(loc, glob, None)
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    assert ex.errors() == 1, "the missing peer must be reported"
+    assert 0.2 < dt < 5.0, dt                                       # bounded by RT_B200_COMM_TIMEOUT_MS, not a hang
+    assert glob.state[0].item() == 3000                             # own row merged, the absent rank counted as empty
+    print("RESULT timeout ok %.2f s" % dt, flush=True)
+else:
+    print("RESULT idle", flush=True)
+dist.barrier()
+ex.close()
+dist.destroy_process_group()
+"""
+
+
+def test_a_missing_peer_times_out_with_a_sticky_error_instead_of_hanging_the_device(tmp_path):
+    script = tmp_path / "timeout_worker.py"
+    script.write_text(TIMEOUT_WORKER)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK="0", MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), RT_REPO=str(REPO), OMP_NUM_THREADS="1", RT_B200_COMM_TIMEOUT_MS="400")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    outs = []
+    for p in procs:
+        out, err = p.communicate(timeout=300)
+        assert p.returncode == 0, err[-3000:]
+        outs.append(out)
+    assert any("RESULT timeout ok" in o for o in outs)
